@@ -1,0 +1,210 @@
+/* nrw.h - C ABI of the B200-native NeuralRecon-W per-ray training core (libnrw.so).
+ *
+ * The reference (zju3dv/NeuralRecon-W) is pure Python: its seam for this path is the
+ * duck-typed Python object NeuconWRenderer (rendering/renderer.py:51-961) plus the
+ * nn.Modules NeuconW (models/neuconw.py:299-376) and NeRF (models/nerf.py:86-184).  This
+ * header declares what a reference-side binding (ctypes) would bind for
+ * each of those entry points.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *   - the caller (PyTorch) owns all memory; the library never allocates device memory;
+ *     scratch is passed in through nrw_ctx_bind and sized by nrw_*_bytes();
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (a void*);
+ *   - return 0 (NRW_OK) or a negative nrw_status; message via nrw_last_error() (thread-local);
+ *   - one process per GPU; a context is bound to the device current at creation.
+ */
+#ifndef NRW_H_
+#define NRW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NRW_API __attribute__((visibility("default")))
+#else
+#define NRW_API
+#endif
+
+typedef enum {
+  NRW_OK = 0,
+  NRW_ERR_ARG = -1,       /* bad argument / unsupported configuration */
+  NRW_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  NRW_ERR_WORKSPACE = -3, /* bound workspace / packed-weight buffer too small */
+  NRW_ERR_STATE = -4      /* call order violated (e.g. render before pack) */
+} nrw_status;
+
+typedef struct nrw_ctx nrw_ctx;
+
+/* GEMM backends: 0 = tcgen05 tensor cores (product path), 1 = fp32 CUDA cores (verification). */
+#define NRW_GEMM_TCGEN05 0
+#define NRW_GEMM_SIMT 1
+
+NRW_API const char* nrw_last_error(void);
+NRW_API int nrw_version(void);
+
+/* ---- parameter layout ------------------------------------------------------------------
+ * All trainable tensors of NeuconWSystem (embedding_a, neuconw, nerf; SURVEY.md 9.4 /
+ * lightning_modules/neuconw_system.py:74-103) live in ONE flat fp32 buffer; gradients in a
+ * second buffer with the same layout (single NCCL all-reduce).  The table below is the
+ * single source of truth for names / shapes / offsets (in floats). */
+typedef struct {
+  const char* name; /* reference state_dict key, e.g. "neuconw.sdf_net.lin0.weight_v" */
+  int rows, cols;   /* cols == 0 for 1-D tensors, rows == cols == 0 for scalars */
+  long long offset; /* float offset into the flat buffer */
+  long long numel;
+} nrw_param_info;
+NRW_API int nrw_param_count(void);
+NRW_API int nrw_param_table(int n_vocab, int n_a, nrw_param_info* out /* host, nrw_param_count() */);
+NRW_API long long nrw_param_total(int n_vocab, int n_a);
+
+/* ---- context ---------------------------------------------------------------------------
+ * n_planes: bf16 operand planes per fp32 tensor (1 = bf16, 2 = bf16x3 products, 3 = bf16x6
+ * products ~ fp32).  chunk_rows: samples per MLP chunk (multiple of 128). */
+NRW_API int nrw_ctx_create(nrw_ctx** out, int n_planes, int gemm_backend, int n_vocab, int n_a);
+NRW_API int nrw_ctx_destroy(nrw_ctx* ctx);
+NRW_API long long nrw_packed_bytes(const nrw_ctx* ctx);
+NRW_API long long nrw_workspace_bytes(const nrw_ctx* ctx, int chunk_rows, int with_backward, int max_rays,
+                                      int max_samples_per_ray);
+NRW_API int nrw_ctx_bind(nrw_ctx* ctx, void* packed, long long packed_bytes, void* workspace,
+                         long long workspace_bytes, int chunk_rows, int with_backward, int max_rays,
+                         int max_samples_per_ray, void* stream);
+/* weight-norm materialisation + bf16 plane split + transposes of every layer (replaces what
+ * torch.nn.utils.weight_norm recomputes on every call, models/neuconw.py:104-105,256-257). */
+NRW_API int nrw_pack_weights(nrw_ctx* ctx, const float* params, void* stream);
+
+/* ---- NeuconWRenderer.sdf / NeuconW.sdf  (rendering/renderer.py:947-949) ----------------- */
+NRW_API int nrw_sdf_query(nrw_ctx* ctx, const float* pts /*[n,3]*/, long long n, float* sdf /*[n]*/,
+                          void* stream);
+/* NeuconW.forward pieces (models/neuconw.py:339-376): sdf, features' consumer rgb, normals. */
+NRW_API int nrw_neuconw_forward(nrw_ctx* ctx, const float* pts /*[n,3]*/, const float* dirs /*[n,3]*/,
+                                const float* a /*[n,n_a]*/, long long n, float* rgb /*[n,3]*/,
+                                float* sdf /*[n]*/, float* normals /*[n,3]*/, void* stream);
+/* NeRF.forward (models/nerf.py:156-182): pts4 [n,4], dirs [n,3], a [n,n_a] -> density[n], rgb[n,3] */
+NRW_API int nrw_nerf_forward(nrw_ctx* ctx, const float* pts4, const float* dirs, const float* a,
+                             long long n, float* density, float* rgb, void* stream);
+
+/* ---- NeuconWRenderer.sparse_sampler (rendering/renderer.py:458-568) ---------------------- */
+typedef struct {
+  int n_samples, n_importance, up_sample_steps, n_outside, s_val_base;
+  int boundary_samples; /* only used when sample_near/sample_far are given */
+  int perturb;          /* 0/1: u_ray / u_out must be given when 1 */
+} nrw_sampler_cfg;
+/* o,d [R,3] (unit-sphere frame), near,far [R]; sample_near/sample_far [R] or NULL (no fine octree);
+ * u_ray [R], u_out [R,n_outside] uniform draws or NULL.  Outputs: z_vals [R,S], z_out [R,n_outside],
+ * sample_dist [R].  Optional trace (may be NULL): inds int32 [steps,R,n_imp/steps] (searchsorted
+ * indices), order int32 [steps,R,S_round_max] (merge permutation). */
+NRW_API int nrw_sample(nrw_ctx* ctx, const nrw_sampler_cfg* cfg, int R, const float* o, const float* d,
+                       const float* near, const float* far, const float* sample_near,
+                       const float* sample_far, const float* u_ray, const float* u_out, float* z_vals,
+                       float* z_out, float* sample_dist, int32_t* trace_inds, int32_t* trace_order,
+                       void* stream);
+NRW_API int nrw_samples_per_ray(const nrw_sampler_cfg* cfg, int with_fine_octree);
+/* one up-sampling round with injected sdf (stage-wise bit-exactness test; renderer.py:257-363) */
+NRW_API int nrw_upsample_round(int R, int m, int n_new, float inv_s, const float* o, const float* d,
+                               const float* z /*[R,m]*/, const float* sdf /*[R,m]*/,
+                               float* cdf_scratch /*[R,m]*/, float* z_new /*[R,n_new]*/,
+                               float* z_merged /*[R,m+n_new]*/, int32_t* inds /*[R,n_new]*/,
+                               int32_t* order /*[R,m+n_new]*/, void* stream);
+
+/* ---- NeuconWRenderer.render core (rendering/renderer.py:157-228,570-783) ----------------- */
+typedef struct {
+  int R, S, n_outside;        /* T = S + n_outside */
+  float cos_anneal_ratio;
+  const float* background_rgb; /* device [3] or NULL (renderer.py:753-754) */
+  int reserved0;
+  int trim_sphere;
+} nrw_render_cfg;
+
+/* Device pointers of one render call.  Inputs first, then outputs, then the small per-sample
+ * tensors the backward pass needs ("saved", caller-allocated like everything else). */
+typedef struct {
+  /* inputs */
+  const float* o;           /* [R,3] */
+  const float* d;           /* [R,3] */
+  const float* z_vals;      /* [R,S] */
+  const float* z_out;       /* [R,n_outside] */
+  const float* sample_dist; /* [R] */
+  const float* a_emb;       /* [R,n_a] */
+  const float* inv_s;       /* [1] */
+  /* outputs (16-key dict of renderer.py:899-916, minus the loss-side glue kept in torch) */
+  float* color;             /* [R,3] */
+  float* color_sphere;      /* [R,3] */
+  float* color_bg;          /* [R,3] */
+  float* cdf;               /* [R,S] */
+  float* gradients;         /* [R,S,3] */
+  float* weights;           /* [R,T] */
+  float* weights_sum;       /* [R] */
+  float* inside_sphere;     /* [R,S] */
+  float* depth;             /* [R] */
+  float* normals;           /* [R,3] */
+  float* gradient_error;    /* [1] */
+  /* saved for backward */
+  float* sv_sdf;            /* [R,S] */
+  float* sv_rgb;            /* [R,S,3] */
+  float* sv_bg_alpha;       /* [R,T] */
+  float* sv_bg_rgb;         /* [R,T,3] */
+  float* sv_z_feed;         /* [R,T] */
+  float* sv_relax_sum;      /* [1] */
+} nrw_render_io;
+
+NRW_API int nrw_render_forward(nrw_ctx* ctx, const nrw_render_cfg* cfg, const nrw_render_io* io, void* stream);
+
+/* upstream gradients (NULL = zero) and gradient outputs */
+typedef struct {
+  const float* g_color;        /* [R,3] */
+  const float* g_color_sphere; /* [R,3] */
+  const float* g_color_bg;     /* [R,3] */
+  const float* g_cdf;          /* [R,S] */
+  const float* g_gradients;    /* [R,S,3] */
+  const float* g_weights;      /* [R,T] */
+  const float* g_weights_sum;  /* [R] */
+  const float* g_depth;        /* [R] */
+  const float* g_normals;      /* [R,3] */
+  const float* g_gradient_error; /* [1] */
+  float* grad_params;          /* flat, same layout as params; ACCUMULATED into */
+  float* grad_a_emb;           /* [R,n_a] (written) */
+  float* grad_inv_s;           /* [1] (written) */
+} nrw_render_grads;
+NRW_API int nrw_render_backward(nrw_ctx* ctx, const nrw_render_cfg* cfg, const nrw_render_io* io,
+                                const nrw_render_grads* g, void* stream);
+
+/* stage-wise compositing (K4) with injected per-sample inputs, for parity tests */
+NRW_API int nrw_composite_forward(const nrw_render_cfg* cfg, const nrw_render_io* io, const float* sdf,
+                                  const float* normals_ps /*[R,S,3]*/, const float* rgb /*[R,S,3]*/,
+                                  const float* bg_alpha, const float* bg_rgb, float* scratch2 /*[2]*/,
+                                  void* stream);
+NRW_API int nrw_composite_backward(const nrw_render_cfg* cfg, const nrw_render_io* io,
+                                   const nrw_render_grads* g, const float* normals_ps, float* d_sdf,
+                                   float* d_normals_ps, float* d_rgb, float* d_bg_alpha, float* d_bg_rgb,
+                                   void* stream);
+
+/* ---- octree near/far (tools/prepare_data/generate_voxel.py:311-439) ---------------------- */
+/* octree bytes (breadth-first, one per non-leaf), prefix = exclusive popcount sum (#nodes entries),
+ * pyramid int32 [2, level+2].  rays in the SfM frame.  Outputs near,far [R] (already * scale),
+ * pid int32 [R] (-1 = miss), count int32 [R] (# leaf voxels hit). */
+NRW_API int nrw_octree_near_far(const uint8_t* octree, const int32_t* prefix, const int32_t* pyramid_host,
+                                int level, const float* rays_o, const float* rays_d, int R,
+                                const float scene_origin[3], float scale, float* near, float* far,
+                                int32_t* pid, int32_t* count, void* stream);
+/* compacted hit list (ray_index, point_index, depth) front-to-back per ray; offsets = exclusive scan of count */
+NRW_API int nrw_octree_hits(const uint8_t* octree, const int32_t* prefix, const int32_t* pyramid_host,
+                            int level, const float* rays_o, const float* rays_d, int R,
+                            const float scene_origin[3], float scale, const int64_t* offsets,
+                            int32_t* ray_index, int32_t* point_index, float* depth, void* stream);
+
+/* ---- unit-test hooks ---------------------------------------------------------------------- */
+/* D[M,N] = (sum planes of A)[M,K] * (sum planes of B)[N,K]^T from fp32 inputs: splits into planes in
+ * scratch (caller-provided, nrw_gemm_test_scratch_bytes) and runs the selected backend. */
+NRW_API long long nrw_gemm_test_scratch_bytes(int M, int N, int K);
+NRW_API int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices, int M, int N, int K,
+                          const float* A, const float* B, const float* bias, int act, float* D,
+                          void* scratch, void* stream);
+NRW_API long long nrw_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRW_H_ */

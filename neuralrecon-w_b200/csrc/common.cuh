@@ -1,0 +1,99 @@
+// Common device/host helpers for the nrw CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/nrw.h"
+
+namespace nrw {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (no exceptions across the C ABI) ---------------------------------
+void set_last_error(const char* fmt, ...);
+#define NRW_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::nrw::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                            cudaGetErrorString(_e));                                   \
+      return NRW_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+#define NRW_CHECK(cond, code, ...)                                                     \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::nrw::set_last_error(__VA_ARGS__);                                              \
+      return code;                                                                     \
+    }                                                                                  \
+  } while (0)
+#define NRW_TRY(expr)                                                                  \
+  do {                                                                                 \
+    int _s = (expr);                                                                   \
+    if (_s != NRW_OK) return _s;                                                       \
+  } while (0)
+#define NRW_LAUNCH_OK() NRW_CUDA_OK(cudaGetLastError())
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---- scalar math shared by epilogues and pointwise kernels ------------------------------
+// torch.nn.Softplus(beta=100, threshold=20) and its first/second derivatives
+// (reference models/neuconw.py:261; autograd formulas of softplus_backward /
+// softplus_double_backward).
+__device__ __forceinline__ float softplus100(float v) {
+  float t = 100.0f * v;
+  return t > 20.0f ? v : log1pf(expf(t)) * 0.01f;
+}
+__device__ __forceinline__ float softplus100_d1(float v) {  // d softplus / dv
+  float t = 100.0f * v;
+  return t > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-t));
+}
+__device__ __forceinline__ float softplus100_d2(float v) {  // d2 softplus / dv2
+  float t = 100.0f * v;
+  if (t > 20.0f) return 0.0f;
+  float s = 1.0f / (1.0f + expf(-t));
+  return 100.0f * s * (1.0f - s);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Split an fp32 value into up to 3 bf16 planes: v ~= p0 + p1 + p2 (p0 = rn(v), ...).
+// With 3 planes the sum is exact for normal-range values (3 x 8 mantissa bits).
+__device__ __forceinline__ void split3(float v, bf16& p0, bf16& p1, bf16& p2) {
+  p0 = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r);
+  r = r - __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r);
+}
+
+// An activation-like matrix stored as n_planes bf16 planes [plane][rows][ld].
+struct Planes {
+  bf16* p;              // plane 0
+  long long pstride;    // elements between planes
+  int ld;               // leading dimension (elements)
+  __host__ __device__ bf16* plane(int i) const { return p + (long long)i * pstride; }
+  __host__ Planes cols(int c) const { return Planes{p + c, pstride, ld}; }
+};
+
+__device__ __forceinline__ float planes_load(const Planes& P, int n_planes, long long idx) {
+  float v = __bfloat162float(P.p[idx]);
+  if (n_planes > 1) v += __bfloat162float(P.p[P.pstride + idx]);
+  if (n_planes > 2) v += __bfloat162float(P.p[2 * P.pstride + idx]);
+  return v;
+}
+__device__ __forceinline__ void planes_store(const Planes& P, int n_planes, long long idx, float v) {
+  bf16 a, b, c;
+  split3(v, a, b, c);
+  P.p[idx] = a;
+  if (n_planes > 1) P.p[P.pstride + idx] = b;
+  if (n_planes > 2) P.p[2 * P.pstride + idx] = c;
+}
+
+}  // namespace nrw

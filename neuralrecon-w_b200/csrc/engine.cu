@@ -1,0 +1,522 @@
+// Chunked orchestration of the per-ray hot path: sampler -> background NeRF -> SDF value/normal ->
+// colour net -> compositing, and the hand-derived backward of all of it.
+// Every dense layer is one tcgen05 GEMM launch with a fused epilogue; chunks of `Mc` samples keep the
+// inter-layer activations L2-resident.  Backward recomputes the forward of a chunk into the workspace
+// and immediately consumes it, so memory is O(chunk) instead of O(batch).
+#include "engine.h"
+
+namespace nrw {
+
+static constexpr float INV_SQRT2 = 0.70710678118654752440f;
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  long long off = 0;
+  bool dry;
+  void* take(long long bytes) {
+    off = round_up(off, 1024);
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+  float* f32(long long n) { return reinterpret_cast<float*>(take(n * 4)); }
+  Planes planes(long long rows, int ld, int P) {
+    const long long ps = round_up(rows * ld, 512);
+    bf16* p = reinterpret_cast<bf16*>(take(ps * P * 2));
+    return Planes{p, ps, ld};
+  }
+};
+
+static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, int max_T) {
+  const int P = c.n_planes;
+  const long long M = Mc;
+  c.PTS = cv.f32(M * 3);
+  c.U0 = cv.planes(M, 64, P);
+  for (int l = 1; l <= 8; ++l) c.U[l] = cv.planes(M, 512, P);
+  for (int l = 0; l < 8; ++l) c.A[l] = cv.f32(M * 512);
+  for (int l = 0; l < 8; ++l) c.G[l] = cv.planes(M, 512, P);
+  c.Q[0] = cv.f32(M * 64);
+  for (int l = 1; l < 8; ++l) c.Q[l] = cv.f32(M * 512);
+  c.FEAT = cv.planes(M, 512, P);
+  c.c_sdf = cv.f32(M);
+  c.c_nrm = cv.f32(M * 3);
+  c.IN1 = cv.planes(M, 640, P);
+  c.H1 = cv.planes(M, 128, P);
+  c.IN2 = cv.planes(M, 192, P);
+  for (int l = 1; l <= 4; ++l) c.X[l] = cv.planes(M, 256, P);
+  c.c_rgb = cv.f32(M * 3);
+  c.IN0 = cv.planes(M, 128, P);
+  for (int l = 1; l <= 8; ++l)
+    if (l != 5) c.NH[l] = cv.planes(M, 256, P);
+  c.IN5 = cv.planes(M, 384, P);
+  c.FEATN = cv.planes(M, 384, P);
+  for (int l = 1; l <= 4; ++l) c.AP[l] = cv.planes(M, 128, P);
+  c.c_density = cv.f32(M);
+  c.c_alpha = cv.f32(M);
+  c.c_rgbbg = cv.f32(M * 3);
+  c.c_dists = cv.f32(M);
+  c.ge_acc = cv.f32(4);
+  if (with_bwd) {
+    c.DQ0 = cv.planes(M, 64, P);
+    c.DQodd = cv.planes(M, 512, P);
+    c.DQeven = cv.planes(M, 512, P);
+    c.DQ4 = cv.planes(M, 512, P);
+    c.DA[0] = cv.planes(M, 512, P);
+    c.DA[1] = cv.planes(M, 512, P);
+    c.DFEAT = cv.planes(M, 512, P);
+    c.DQ8f = cv.f32(M * 512);
+    for (int l = 0; l < 8; ++l) c.DA2[l] = cv.f32(M * 512);
+    c.dX[0] = cv.planes(M, 256, P);
+    c.dX[1] = cv.planes(M, 256, P);
+    c.dH2 = cv.planes(M, 128, P);
+    c.dH1 = cv.planes(M, 128, P);
+    c.dXF = cv.planes(M, 512, P);
+    c.dNA[0] = cv.planes(M, 128, P);
+    c.dNA[1] = cv.planes(M, 128, P);
+    c.dNF = cv.planes(M, 256, P);
+    c.dNH[0] = cv.planes(M, 256, P);
+    c.dNH[1] = cv.planes(M, 256, P);
+    c.tail = cv.f32(M * 128);
+    c.c_dn = cv.f32(M * 3);
+    c.c_ddens = cv.f32(M);
+    c.gs = cv.f32(c.pm.grad_floats);
+  }
+  const long long RT = (long long)max_rays * max_T;
+  for (int i = 0; i < 2; ++i) { c.gz[i] = cv.f32(RT); c.gsdf[i] = cv.f32(RT); }
+  c.gznew = cv.f32(RT);
+  c.gsdfnew = cv.f32(RT);
+  c.gcdf = cv.f32(RT);
+  c.gorder = reinterpret_cast<int32_t*>(cv.f32(RT));
+  c.g_pts = cv.f32(RT * 3);
+  if (with_bwd) {
+    c.g_dsdf = cv.f32(RT);
+    c.g_dnrm = cv.f32(RT * 3);
+    c.g_drgb = cv.f32(RT * 3);
+    c.g_dbga = cv.f32(RT);
+    c.g_dbgc = cv.f32(RT * 3);
+  }
+}
+
+long long workspace_bytes(const nrw_ctx& c0, int chunk_rows, int with_bwd, int max_rays, int max_T) {
+  nrw_ctx c = c0;
+  Carver cv{nullptr, 0, true};
+  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T);
+  return round_up(cv.off, 1024) + 1024;
+}
+
+int carve_workspace(nrw_ctx& c, void* base, long long bytes, int chunk_rows, int with_bwd, int max_rays,
+                    int max_T, cudaStream_t s) {
+  NRW_CHECK(chunk_rows >= 128 && chunk_rows % 128 == 0, NRW_ERR_ARG, "chunk_rows=%d must be a multiple of 128", chunk_rows);
+  NRW_CHECK((reinterpret_cast<uintptr_t>(base) & 255) == 0, NRW_ERR_ARG, "workspace must be 256B aligned");
+  const long long need = workspace_bytes(c, chunk_rows, with_bwd, max_rays, max_T);
+  NRW_CHECK(bytes >= need, NRW_ERR_WORKSPACE, "workspace too small: %lld < %lld bytes", bytes, need);
+  char* b = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~uintptr_t(1023));
+  Carver cv{b, 0, false};
+  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T);
+  // zero once: padding columns / never-written tails must be finite (they meet zero weights)
+  NRW_CUDA_OK(cudaMemsetAsync(b, 0, cv.off, s));
+  c.Mc = chunk_rows; c.with_bwd = with_bwd; c.max_rays = max_rays; c.max_T = max_T;
+  c.bound = true;
+  return NRW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM helpers
+// ---------------------------------------------------------------------------------------------
+static int mm(nrw_ctx& c, Planes A, Planes B, int M, int N, int K, Epi e, cudaStream_t s) {
+  GemmDesc g;
+  g.A = A; g.B = B; g.n_planes = c.n_planes; g.M = M; g.N = N; g.K = K; g.mn_major = 0; g.k_slices = 1;
+  if (e.out_pl.p) e.n_planes = c.n_planes;
+  g.epi = e;
+  return gemm(c.backend, g, s);
+}
+// dW[layer] += dY^T X   (dY [M, Np], X [M, Kx]); atomically accumulated into the gradient scratch
+static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t s) {
+  const PackedLayer& L = c.pm.layers[layer];
+  GemmDesc g;
+  g.A = dY; g.B = X; g.n_planes = c.n_planes;
+  g.M = L.Np; g.N = L.Kp; g.K = M; g.mn_major = 1;
+  const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.n_planes >= 2) ? 128 : 256);
+  const int tiles = cdiv(g.M, 128) * cdiv(g.N, bn);
+  int ks = 296 / tiles;
+  const int max_ks = M / 512 > 0 ? M / 512 : 1;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  // avoid empty trailing slices
+  const int kb_total = cdiv(M, 64);
+  const int kb_per = cdiv(kb_total, ks);
+  ks = cdiv(kb_total, kb_per);
+  g.k_slices = ks;
+  Epi e;
+  e.out_f32 = c.dW(layer); e.ld_f32 = L.Kp; e.atomic = 1;
+  g.epi = e;
+  return gemm(c.backend, g, s);
+}
+static int bias_grad(nrw_ctx& c, Planes dY, int M, int layer, cudaStream_t s) {
+  return launch_colsum(dY, c.n_planes, nullptr, 0, M, c.pm.layers[layer].Np, nullptr, c.db(layer), nullptr, s);
+}
+static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld, P.pstride, P.ld}; }
+
+// ---------------------------------------------------------------------------------------------
+// forward chunks
+// ---------------------------------------------------------------------------------------------
+int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, bool need_feat, cudaStream_t s) {
+  const int P = c.n_planes;
+  NRW_TRY(launch_sdf_embed(pts, M, P, c.U0, c.U[4], s));
+  for (int l = 0; l < 8; ++l) {
+    Epi e;
+    e.bias = c.bias(L_SDF0 + l);
+    e.act = ACT_SOFTPLUS100;
+    if (need_normal || l == 7) { e.out_pre = c.A[l]; e.ld_pre = 512; }
+    e.out_pl = c.U[l + 1];
+    if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
+    NRW_TRY(mm(c, l == 0 ? c.U0 : c.U[l], c.W(L_SDF0 + l), M, 512, l == 0 ? 64 : 512, e, s));
+  }
+  const float* w0 = c.f_area + c.pm.heads.sdf_w0;
+  const float* b0 = c.f_area + c.pm.heads.sdf_b0;
+  NRW_TRY(launch_sdf_head(c.A[7], M, w0, b0, c.c_sdf, P, need_normal ? c.G[7] : Planes{nullptr, 0, 0}, s));
+  if (need_feat) {
+    Epi e;
+    e.bias = c.bias(L_SDF8F);
+    e.out_pl = c.FEAT;
+    NRW_TRY(mm(c, c.U[8], c.W(L_SDF8F), M, 512, 512, e, s));
+  }
+  if (need_normal) {
+    for (int l = 7; l >= 1; --l) {
+      Epi e;
+      e.out_pre = c.Q[l]; e.ld_pre = 512;
+      e.aux_sig = c.A[l - 1]; e.ld_aux = 512;
+      e.out_pl = c.G[l - 1];
+      if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }
+      NRW_TRY(mm(c, c.G[l], c.WT(L_SDF0 + l), M, 512, 512, e, s));
+    }
+    Epi e;
+    e.out_pre = c.Q[0]; e.ld_pre = 64;
+    NRW_TRY(mm(c, c.G[0], c.WT(L_SDF0), M, 64, 512, e, s));
+    NRW_TRY(launch_sdf_normal(pts, c.Q[0], c.Q[4], M, c.c_nrm, s));
+  }
+  return NRW_OK;
+}
+
+int color_chunk_forward(nrw_ctx& c, int M, const float* pts, const float* dirs, const float* a, int rows_per_src,
+                        cudaStream_t s) {
+  const int P = c.n_planes;
+  NRW_TRY(launch_color_embed(dirs, a, c.n_a, rows_per_src, pts, c.c_nrm, M, P, c.IN1, c.IN2, s));
+  { Epi e; e.bias = c.bias(L_CX); e.out_pl = c.IN1; NRW_TRY(mm(c, c.FEAT, c.W(L_CX), M, 512, 512, e, s)); }
+  { Epi e; e.bias = c.bias(L_CS0); e.act = ACT_RELU; e.out_pl = c.H1; NRW_TRY(mm(c, c.IN1, c.W(L_CS0), M, 128, 640, e, s)); }
+  { Epi e; e.bias = c.bias(L_CS1); e.act = ACT_RELU; e.out_pl = c.IN2; NRW_TRY(mm(c, c.H1, c.W(L_CS1), M, 128, 128, e, s)); }
+  { Epi e; e.bias = c.bias(L_CL0); e.act = ACT_RELU; e.out_pl = c.X[1]; NRW_TRY(mm(c, c.IN2, c.W(L_CL0), M, 256, 192, e, s)); }
+  for (int l = 1; l <= 3; ++l) {
+    Epi e; e.bias = c.bias(L_CL0 + l); e.act = ACT_RELU; e.out_pl = c.X[l + 1];
+    NRW_TRY(mm(c, c.X[l], c.W(L_CL0 + l), M, 256, 256, e, s));
+  }
+  NRW_TRY(launch_head(3, c.X[4], P, 256, M, c.f_area + c.pm.heads.cl4_w, c.f_area + c.pm.heads.cl4_b, ACT_SIGMOID,
+                      nullptr, c.c_rgb, nullptr, s));
+  return NRW_OK;
+}
+
+int nerf_chunk_forward(nrw_ctx& c, int M, const float* o, const float* d, const float* z, const float* sdist,
+                       const float* pts4, const float* a, int T, int rows_per_src, cudaStream_t s) {
+  const int P = c.n_planes;
+  NRW_TRY(launch_nerf_embed(o, d, z, sdist, pts4, a, c.n_a, T, rows_per_src, M, P, c.IN0, c.IN5, c.FEATN,
+                            pts4 ? nullptr : c.c_dists, s));
+  { Epi e; e.bias = c.bias(L_N0); e.act = ACT_RELU; e.out_pl = c.NH[1]; NRW_TRY(mm(c, c.IN0, c.W(L_N0), M, 256, 128, e, s)); }
+  for (int l = 1; l <= 3; ++l) {
+    Epi e; e.bias = c.bias(L_N0 + l); e.act = ACT_RELU; e.out_pl = c.NH[l + 1];
+    NRW_TRY(mm(c, c.NH[l], c.W(L_N0 + l), M, 256, 256, e, s));
+  }
+  { Epi e; e.bias = c.bias(L_N0 + 4); e.act = ACT_RELU; e.out_pl = c.IN5; NRW_TRY(mm(c, c.NH[4], c.W(L_N0 + 4), M, 256, 256, e, s)); }
+  { Epi e; e.bias = c.bias(L_N0 + 5); e.act = ACT_RELU; e.out_pl = c.NH[6]; NRW_TRY(mm(c, c.IN5, c.W(L_N0 + 5), M, 256, 384, e, s)); }
+  for (int l = 6; l <= 7; ++l) {
+    Epi e; e.bias = c.bias(L_N0 + l); e.act = ACT_RELU; e.out_pl = c.NH[l + 1];
+    NRW_TRY(mm(c, c.NH[l], c.W(L_N0 + l), M, 256, 256, e, s));
+  }
+  NRW_TRY(launch_head(1, c.NH[8], P, 256, M, c.f_area + c.pm.heads.na_w, c.f_area + c.pm.heads.na_b, ACT_NONE,
+                      pts4 ? nullptr : c.c_dists, pts4 ? c.c_density : c.c_alpha, pts4 ? nullptr : c.c_density, s));
+  { Epi e; e.bias = c.bias(L_NF); e.out_pl = c.FEATN; NRW_TRY(mm(c, c.NH[8], c.W(L_NF), M, 256, 256, e, s)); }
+  { Epi e; e.bias = c.bias(L_NS0); e.act = ACT_RELU; e.out_pl = c.AP[1]; NRW_TRY(mm(c, c.FEATN, c.W(L_NS0), M, 128, 384, e, s)); }
+  for (int l = 1; l <= 3; ++l) {
+    Epi e; e.bias = c.bias(L_NS0 + l); e.act = ACT_RELU; e.out_pl = c.AP[l + 1];
+    NRW_TRY(mm(c, c.AP[l], c.W(L_NS0 + l), M, 128, 128, e, s));
+  }
+  NRW_TRY(launch_head(3, c.AP[4], P, 128, M, c.f_area + c.pm.heads.nr_w, c.f_area + c.pm.heads.nr_b, ACT_NONE, nullptr,
+                      c.c_rgbbg, nullptr, s));
+  return NRW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward chunks
+// ---------------------------------------------------------------------------------------------
+__global__ void add_normal_grad_kernel(float* __restrict__ dn, const float* __restrict__ src,
+                                       const float* __restrict__ tail, int M) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) dn[m * 3 + ch] = src[m * 3 + ch] + tail[(long long)m * 64 + 3 + ch];
+}
+
+// d_rgb: [M,3] upstream gradient of the colour output.  Produces DFEAT (planes), c_dn (normal gradient
+// = d_nrm_comp + colour-net contribution) and accumulates per-ray appearance-code gradients.
+int color_chunk_backward(nrw_ctx& c, int M, const float* d_rgb, const float* d_nrm_comp, int rows_per_src,
+                         float* d_a_rays, int R_chunk, cudaStream_t s) {
+  const int P = c.n_planes;
+  const Heads& H = c.pm.heads;
+  NRW_TRY(launch_head_bwd(3, c.X[4], P, 256, M, c.f_area + H.cl4_w, d_rgb, c.c_rgb, nullptr, 1, c.dX[0], nullptr,
+                          c.gs + H.d_cl4_w, c.gs + H.d_cl4_b, s));
+  int cur = 0;
+  for (int l = 3; l >= 1; --l) {
+    NRW_TRY(mm_dw(c, c.dX[cur], c.X[l], M, L_CL0 + l, s));
+    NRW_TRY(bias_grad(c, c.dX[cur], M, L_CL0 + l, s));
+    Epi e; e.aux_relu = c.X[l].p; e.ld_relu = 256; e.out_pl = c.dX[1 - cur];
+    NRW_TRY(mm(c, c.dX[cur], c.WT(L_CL0 + l), M, 256, 256, e, s));
+    cur = 1 - cur;
+  }
+  NRW_TRY(mm_dw(c, c.dX[cur], c.IN2, M, L_CL0, s));
+  NRW_TRY(bias_grad(c, c.dX[cur], M, L_CL0, s));
+  { Epi e; e.aux_relu = c.IN2.p; e.ld_relu = 192; e.out_pl = c.dH2;
+    NRW_TRY(mm(c, c.dX[cur], c.WT(L_CL0), M, 128, 256, e, s)); }
+  { Epi e; e.out_f32 = c.tail; e.ld_f32 = 64;
+    NRW_TRY(mm(c, c.dX[cur], rows(c.WT(L_CL0), 128), M, 64, 256, e, s)); }
+  add_normal_grad_kernel<<<cdiv(M, 256), 256, 0, s>>>(c.c_dn, d_nrm_comp, c.tail, M);
+  NRW_LAUNCH_OK();
+  // static_linear_1: H1 -> IN2[:, :128]
+  NRW_TRY(mm_dw(c, c.dH2, c.H1, M, L_CS1, s));
+  NRW_TRY(bias_grad(c, c.dH2, M, L_CS1, s));
+  { Epi e; e.aux_relu = c.H1.p; e.ld_relu = 128; e.out_pl = c.dH1;
+    NRW_TRY(mm(c, c.dH2, c.WT(L_CS1), M, 128, 128, e, s)); }
+  // static_linear_0: IN1 [xf | viewPE | a] -> H1
+  NRW_TRY(mm_dw(c, c.dH1, c.IN1, M, L_CS0, s));
+  NRW_TRY(bias_grad(c, c.dH1, M, L_CS0, s));
+  { Epi e; e.out_pl = c.dXF; NRW_TRY(mm(c, c.dH1, c.WT(L_CS0), M, 512, 128, e, s)); }
+  { Epi e; e.out_f32 = c.tail; e.ld_f32 = 128;
+    NRW_TRY(mm(c, c.dH1, rows(c.WT(L_CS0), 512), M, 128, 128, e, s)); }
+  if (d_a_rays) NRW_TRY(launch_segsum(c.tail, 128, 27, c.n_a, R_chunk, rows_per_src, d_a_rays, 1, s));
+  // xyz_encoding_final: FEAT -> IN1[:, :512]
+  NRW_TRY(mm_dw(c, c.dXF, c.FEAT, M, L_CX, s));
+  NRW_TRY(bias_grad(c, c.dXF, M, L_CX, s));
+  { Epi e; e.out_pl = c.DFEAT; NRW_TRY(mm(c, c.dXF, c.WT(L_CX), M, 512, 512, e, s)); }
+  return NRW_OK;
+}
+
+static Planes dq_buf(nrw_ctx& c, int l) {
+  if (l == 0) return c.DQ0;
+  if (l == 4) return c.DQ4;
+  return (l & 1) ? c.DQodd : c.DQeven;
+}
+
+// d_sdf [M], c.c_dn [M,3], c.DFEAT -> parameter gradients of the SDF net (second-order backward)
+int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, cudaStream_t s) {
+  const int P = c.n_planes;
+  const Heads& H = c.pm.heads;
+  const float* w0 = c.f_area + H.sdf_w0;
+  NRW_TRY(launch_sdf_normal_bwd(pts, c.c_dn, M, P, c.DQ0, c.DQ4, s));
+  // tangent sweep: derivative of the gradient chain
+  for (int l = 0; l < 8; ++l) {
+    Planes DQl = dq_buf(c, l);
+    NRW_TRY(mm_dw(c, c.G[l], DQl, M, L_SDF0 + l, s));
+    Epi e;
+    e.aux_sig = c.A[l]; e.ld_aux = 512;
+    if (l == 7) { e.aux_q = w0; e.aux_q_bcast = 1; } else { e.aux_q = c.Q[l + 1]; }
+    e.out2 = c.DA2[l]; e.ld_out2 = 512;
+    if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
+    if (l < 7) e.out_pl = dq_buf(c, l + 1);
+    else { e.out_f32 = c.DQ8f; e.ld_f32 = 512; }
+    NRW_TRY(mm(c, DQl, c.W(L_SDF0 + l), M, 512, l == 0 ? 64 : 512, e, s));
+  }
+  NRW_TRY(launch_colsum(Planes{nullptr, 0, 0}, P, c.DQ8f, 512, M, 512, nullptr, c.gs + H.d_sdf_w0, nullptr, s));
+  // reverse sweep
+  NRW_TRY(mm_dw(c, c.DFEAT, c.U[8], M, L_SDF8F, s));
+  NRW_TRY(bias_grad(c, c.DFEAT, M, L_SDF8F, s));
+  NRW_TRY(launch_colsum(c.U[8], P, nullptr, 0, M, 512, d_sdf, c.gs + H.d_sdf_w0, c.gs + H.d_sdf_b0, s));
+  {
+    Epi e;
+    e.rowvec = d_sdf; e.colvec = w0;
+    e.aux_sig = c.A[7]; e.aux_add = c.DA2[7]; e.ld_aux = 512;
+    e.out_pl = c.DA[1];
+    NRW_TRY(mm(c, c.DFEAT, c.WT(L_SDF8F), M, 512, 512, e, s));
+  }
+  for (int l = 7; l >= 1; --l) {
+    Planes cur = c.DA[l & 1];
+    NRW_TRY(mm_dw(c, cur, c.U[l], M, L_SDF0 + l, s));
+    NRW_TRY(bias_grad(c, cur, M, L_SDF0 + l, s));
+    Epi e;
+    e.aux_sig = c.A[l - 1]; e.aux_add = c.DA2[l - 1]; e.ld_aux = 512;
+    e.out_pl = c.DA[(l - 1) & 1];
+    if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }
+    NRW_TRY(mm(c, cur, c.WT(L_SDF0 + l), M, 512, 512, e, s));
+  }
+  NRW_TRY(mm_dw(c, c.DA[0], c.U0, M, L_SDF0, s));
+  NRW_TRY(bias_grad(c, c.DA[0], M, L_SDF0, s));
+  return NRW_OK;
+}
+
+int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bgc, float* d_a_rays, int R_chunk,
+                        int T, cudaStream_t s) {
+  const int P = c.n_planes;
+  const Heads& H = c.pm.heads;
+  NRW_TRY(launch_head_bwd(3, c.AP[4], P, 128, M, c.f_area + H.nr_w, d_bgc, nullptr, nullptr, 0, c.dNA[0], nullptr,
+                          c.gs + H.d_nr_w, c.gs + H.d_nr_b, s));
+  int cur = 0;
+  for (int l = 3; l >= 1; --l) {
+    NRW_TRY(mm_dw(c, c.dNA[cur], c.AP[l], M, L_NS0 + l, s));
+    NRW_TRY(bias_grad(c, c.dNA[cur], M, L_NS0 + l, s));
+    Epi e; e.aux_relu = c.AP[l].p; e.ld_relu = 128; e.out_pl = c.dNA[1 - cur];
+    NRW_TRY(mm(c, c.dNA[cur], c.WT(L_NS0 + l), M, 128, 128, e, s));
+    cur = 1 - cur;
+  }
+  NRW_TRY(mm_dw(c, c.dNA[cur], c.FEATN, M, L_NS0, s));
+  NRW_TRY(bias_grad(c, c.dNA[cur], M, L_NS0, s));
+  { Epi e; e.out_pl = c.dNF; NRW_TRY(mm(c, c.dNA[cur], c.WT(L_NS0), M, 256, 128, e, s)); }
+  { Epi e; e.out_f32 = c.tail; e.ld_f32 = 128;
+    NRW_TRY(mm(c, c.dNA[cur], rows(c.WT(L_NS0), 256), M, 128, 128, e, s)); }
+  if (d_a_rays) NRW_TRY(launch_segsum(c.tail, 128, 27, c.n_a, R_chunk, T, d_a_rays, 1, s));
+  // alpha head -> d_density
+  NRW_TRY(launch_head_bwd(1, c.NH[8], P, 256, M, c.f_area + H.na_w, d_bga, c.c_density, c.c_dists, 2,
+                          Planes{nullptr, 0, 0}, c.c_ddens, c.gs + H.d_na_w, c.gs + H.d_na_b, s));
+  // feature_linear: NH[8] -> FEATN[:, :256]
+  NRW_TRY(mm_dw(c, c.dNF, c.NH[8], M, L_NF, s));
+  NRW_TRY(bias_grad(c, c.dNF, M, L_NF, s));
+  { Epi e; e.rowvec = c.c_ddens; e.colvec = c.f_area + H.na_w; e.aux_relu = c.NH[8].p; e.ld_relu = 256;
+    e.out_pl = c.dNH[0];
+    NRW_TRY(mm(c, c.dNF, c.WT(L_NF), M, 256, 256, e, s)); }
+  cur = 0;
+  for (int l = 7; l >= 1; --l) {
+    Planes Xin = (l == 5) ? c.IN5 : c.NH[l];
+    NRW_TRY(mm_dw(c, c.dNH[cur], Xin, M, L_N0 + l, s));
+    NRW_TRY(bias_grad(c, c.dNH[cur], M, L_N0 + l, s));
+    Epi e; e.aux_relu = Xin.p; e.ld_relu = Xin.ld; e.out_pl = c.dNH[1 - cur];
+    NRW_TRY(mm(c, c.dNH[cur], c.WT(L_N0 + l), M, 256, 256, e, s));  // first 256 WT rows = the h part for l==5
+    cur = 1 - cur;
+  }
+  NRW_TRY(mm_dw(c, c.dNH[cur], c.IN0, M, L_N0, s));
+  NRW_TRY(bias_grad(c, c.dNH[cur], M, L_N0, s));
+  return NRW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// public operations
+// ---------------------------------------------------------------------------------------------
+int sdf_query(nrw_ctx& c, const float* pts, long long n, float* sdf, cudaStream_t s) {
+  for (long long i = 0; i < n; i += c.Mc) {
+    const int M = (int)((n - i) < c.Mc ? (n - i) : c.Mc);
+    NRW_TRY(sdf_chunk_forward(c, M, pts + i * 3, false, false, s));
+    NRW_CUDA_OK(cudaMemcpyAsync(sdf + i, c.c_sdf, (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return NRW_OK;
+}
+
+int sample(nrw_ctx& c, const nrw_sampler_cfg& cfg, int R, const float* o, const float* d, const float* near,
+           const float* far, const float* s_near, const float* s_far, const float* u_ray, const float* u_out,
+           float* z_vals, float* z_out, float* sample_dist, int32_t* trace_inds, int32_t* trace_order,
+           cudaStream_t s) {
+  const int n_s = cfg.n_samples, k = cfg.up_sample_steps;
+  const int n_new = (cfg.n_importance > 0 && k > 0) ? cfg.n_importance / k : 0;
+  const int S0 = n_s + k * n_new;
+  const bool fine = s_near != nullptr && cfg.boundary_samples > 0;
+  const int S = S0 + (fine ? cfg.boundary_samples : 0);
+  NRW_CHECK(R <= c.max_rays && S + cfg.n_outside <= c.max_T, NRW_ERR_WORKSPACE,
+            "sample: R=%d S=%d exceed the bound workspace (%d rays x %d)", R, S, c.max_rays, c.max_T);
+  NRW_CHECK(!cfg.perturb || u_ray, NRW_ERR_ARG, "sample: perturb needs u_ray");
+  NRW_TRY(launch_coarse_z(cfg, R, near, far, s_near, s_far, u_ray, u_out, c.gz[0], z_out, sample_dist, s));
+  int cur = 0, m = n_s;
+  if (n_new > 0) {
+    NRW_TRY(launch_points(o, d, c.gz[0], nullptr, R, n_s, 0, c.g_pts, s));
+    NRW_TRY(sdf_query(c, c.g_pts, (long long)R * n_s, c.gsdf[0], s));
+    long long off_i = 0, off_o = 0;
+    for (int i = 0; i < k; ++i) {
+      const float inv_s = 64.0f * (float)(1 << (cfg.s_val_base + i));
+      int32_t* order = trace_order ? trace_order + off_o : c.gorder;
+      NRW_TRY(launch_upsample_round(R, m, n_new, inv_s, o, d, c.gz[cur], c.gsdf[cur], c.gcdf, c.gznew,
+                                    c.gz[1 - cur], trace_inds ? trace_inds + off_i : nullptr, order, s));
+      if (i + 1 < k) {
+        NRW_TRY(launch_points(o, d, c.gznew, nullptr, R, n_new, 0, c.g_pts, s));
+        NRW_TRY(sdf_query(c, c.g_pts, (long long)R * n_new, c.gsdfnew, s));
+        NRW_TRY(launch_merge_sdf(R, m, n_new, c.gsdf[cur], c.gsdfnew, order, c.gsdf[1 - cur], s));
+      }
+      off_i += (long long)R * n_new;
+      off_o += (long long)R * (m + n_new);
+      m += n_new;
+      cur = 1 - cur;
+    }
+  }
+  if (fine) {
+    NRW_TRY(launch_boundary(R, S0, cfg.boundary_samples, near, far, c.gz[cur], z_vals, s));
+  } else {
+    NRW_CUDA_OK(cudaMemcpyAsync(z_vals, c.gz[cur], (size_t)R * S0 * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return NRW_OK;
+}
+
+int render_forward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& io, cudaStream_t s) {
+  const int R = cfg.R, S = cfg.S, T = cfg.S + cfg.n_outside;
+  NRW_CHECK(c.bound && c.packed_valid, NRW_ERR_STATE, "render_forward: bind a workspace and pack weights first");
+  NRW_CHECK(R <= c.max_rays && T <= c.max_T, NRW_ERR_WORKSPACE, "render: R=%d T=%d exceed bound workspace", R, T);
+  NRW_CHECK(c.Mc >= T, NRW_ERR_WORKSPACE, "render: chunk_rows=%d smaller than one ray (%d)", c.Mc, T);
+  const bool bg = cfg.n_outside > 0;
+  if (bg) {
+    NRW_TRY(launch_merge_sorted(R, S, cfg.n_outside, io.z_vals, io.z_out, io.sv_z_feed, s));
+    const int rc = c.Mc / T;
+    for (int r0 = 0; r0 < R; r0 += rc) {
+      const int nr = (R - r0) < rc ? (R - r0) : rc;
+      const int M = nr * T;
+      NRW_TRY(nerf_chunk_forward(c, M, io.o + r0 * 3, io.d + r0 * 3, io.sv_z_feed + (long long)r0 * T,
+                                 io.sample_dist + r0, nullptr, io.a_emb + (long long)r0 * c.n_a, T, T, s));
+      NRW_CUDA_OK(cudaMemcpyAsync(io.sv_bg_alpha + (long long)r0 * T, c.c_alpha, (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
+      NRW_CUDA_OK(cudaMemcpyAsync(io.sv_bg_rgb + (long long)r0 * T * 3, c.c_rgbbg, (size_t)M * 12, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  const int rc = c.Mc / S;
+  for (int r0 = 0; r0 < R; r0 += rc) {
+    const int nr = (R - r0) < rc ? (R - r0) : rc;
+    const int M = nr * S;
+    NRW_TRY(launch_points(io.o + r0 * 3, io.d + r0 * 3, io.z_vals + (long long)r0 * S, io.sample_dist + r0, nr, S, 1, c.PTS, s));
+    NRW_TRY(sdf_chunk_forward(c, M, c.PTS, true, true, s));
+    NRW_TRY(color_chunk_forward(c, M, c.PTS, io.d + r0 * 3, io.a_emb + (long long)r0 * c.n_a, S, s));
+    NRW_CUDA_OK(cudaMemcpyAsync(io.sv_sdf + (long long)r0 * S, c.c_sdf, (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
+    NRW_CUDA_OK(cudaMemcpyAsync(io.gradients + (long long)r0 * S * 3, c.c_nrm, (size_t)M * 12, cudaMemcpyDeviceToDevice, s));
+    NRW_CUDA_OK(cudaMemcpyAsync(io.sv_rgb + (long long)r0 * S * 3, c.c_rgb, (size_t)M * 12, cudaMemcpyDeviceToDevice, s));
+  }
+  return composite_forward(cfg, io, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
+                           bg ? io.sv_bg_rgb : nullptr, c.ge_acc, s);
+}
+
+int render_backward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& io, const nrw_render_grads& g,
+                    cudaStream_t s) {
+  const int R = cfg.R, S = cfg.S, T = cfg.S + cfg.n_outside;
+  NRW_CHECK(c.bound && c.packed_valid && c.with_bwd, NRW_ERR_STATE, "render_backward: workspace not bound for backward");
+  NRW_CHECK(R <= c.max_rays && T <= c.max_T, NRW_ERR_WORKSPACE, "render: R=%d T=%d exceed bound workspace", R, T);
+  const bool bg = cfg.n_outside > 0;
+  NRW_CUDA_OK(cudaMemsetAsync(c.gs, 0, (size_t)c.pm.grad_floats * 4, s));
+  NRW_CUDA_OK(cudaMemsetAsync(g.grad_a_emb, 0, (size_t)R * c.n_a * 4, s));
+  NRW_TRY(composite_backward(cfg, io, g, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
+                             bg ? io.sv_bg_rgb : nullptr, c.g_dsdf, c.g_dnrm, c.g_drgb, bg ? c.g_dbga : nullptr,
+                             bg ? c.g_dbgc : nullptr, g.grad_inv_s, s));
+  if (bg) {
+    const int rc = c.Mc / T;
+    for (int r0 = 0; r0 < R; r0 += rc) {
+      const int nr = (R - r0) < rc ? (R - r0) : rc;
+      const int M = nr * T;
+      NRW_TRY(nerf_chunk_forward(c, M, io.o + r0 * 3, io.d + r0 * 3, io.sv_z_feed + (long long)r0 * T,
+                                 io.sample_dist + r0, nullptr, io.a_emb + (long long)r0 * c.n_a, T, T, s));
+      NRW_TRY(nerf_chunk_backward(c, M, c.g_dbga + (long long)r0 * T, c.g_dbgc + (long long)r0 * T * 3,
+                                  g.grad_a_emb + (long long)r0 * c.n_a, nr, T, s));
+    }
+  }
+  const int rc = c.Mc / S;
+  for (int r0 = 0; r0 < R; r0 += rc) {
+    const int nr = (R - r0) < rc ? (R - r0) : rc;
+    const int M = nr * S;
+    NRW_TRY(launch_points(io.o + r0 * 3, io.d + r0 * 3, io.z_vals + (long long)r0 * S, io.sample_dist + r0, nr, S, 1, c.PTS, s));
+    NRW_TRY(sdf_chunk_forward(c, M, c.PTS, true, true, s));
+    NRW_TRY(color_chunk_forward(c, M, c.PTS, io.d + r0 * 3, io.a_emb + (long long)r0 * c.n_a, S, s));
+    NRW_TRY(color_chunk_backward(c, M, c.g_drgb + (long long)r0 * S * 3, c.g_dnrm + (long long)r0 * S * 3, S,
+                                 g.grad_a_emb + (long long)r0 * c.n_a, nr, s));
+    NRW_TRY(sdf_chunk_backward(c, M, c.PTS, c.g_dsdf + (long long)r0 * S, s));
+  }
+  return unpack_grads(c.pm, c.tab, c.params, c.packed, c.gs, g.grad_params, s);
+}
+
+}  // namespace nrw

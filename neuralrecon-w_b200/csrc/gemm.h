@@ -1,0 +1,33 @@
+// GEMM front-end: D[M,N] = sum over plane products of A_p * B_q^T, fused epilogue (epilogue.cuh).
+#pragma once
+#include "epilogue.cuh"
+
+namespace nrw {
+
+struct GemmDesc {
+  Planes A;           // mn_major=0: [M,K] rows, K contiguous.  mn_major=1: [K,M] rows, M contiguous
+  Planes B;           // mn_major=0: [N,K] rows, K contiguous.  mn_major=1: [K,N] rows, N contiguous
+  int n_planes = 1;   // split-precision planes used from A and B (1, 2 or 3)
+  int M = 0, N = 0, K = 0;
+  int mn_major = 0;
+  int k_slices = 1;   // split-K (epilogue must be atomic)
+  Epi epi;
+};
+
+enum GemmBackend { GEMM_TCGEN05 = 0, GEMM_SIMT = 1 };
+
+// tcgen05 / TMEM / TMA implementation (gemm_tc.cu)
+int gemm_tc(const GemmDesc& g, cudaStream_t stream);
+// fp32 CUDA-core implementation over the same operands (gemm_simt.cu); verification backend
+int gemm_simt(const GemmDesc& g, cudaStream_t stream);
+
+inline int gemm(int backend, const GemmDesc& g, cudaStream_t stream) {
+  return backend == GEMM_SIMT ? gemm_simt(g, stream) : gemm_tc(g, stream);
+}
+
+// number of (a_plane, b_plane) products issued for a given plane count: 1, 3, 6
+inline int n_products(int n_planes) { return n_planes == 1 ? 1 : (n_planes == 2 ? 3 : 6); }
+
+long long gemm_tc_launch_count();
+
+}  // namespace nrw

@@ -1,0 +1,449 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with split-bf16 operand planes and a fused epilogue.
+//
+//   D[M,N] (fp32, TMEM) = sum_{(pa,pb) in products(n_planes)}  A_pa[M,K] * B_pb[N,K]^T
+//
+// * operands are bf16 planes (hi / lo / lo2) of fp32 tensors; n_planes=1 is plain bf16,
+//   n_planes=2 issues hi*hi + hi*lo + lo*hi (~16 mantissa bits), n_planes=3 all six
+//   products whose weight is >= 2^-16 (~fp32).  All products accumulate into the same fp32
+//   TMEM accumulator, so precision is a loop bound, not a different kernel.
+// * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
+//   issuer (single elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN),
+//   warp 2 = TMEM allocator, warps 4.. = epilogue (tcgen05.ld 32x32b -> registers ->
+//   epi_apply -> global).  smem ring of TMA stages (128B swizzle), double-buffered TMEM
+//   accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// * mn_major=1 consumes both operands "transposed" straight from their natural row-major
+//   [rows=K][cols=M|N] layout (MN-major UMMA descriptors) - used for weight gradients
+//   dW = dY^T X with split-K over the sample dimension and fp32 atomics in the epilogue.
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.h"
+
+namespace nrw {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+static constexpr int STAGE_BUDGET = 192 * 1024;
+static constexpr int MAX_STAGES = 8;
+static constexpr int N_EPI_WARPS = 8;
+static constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
+static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256;
+
+struct TcParams {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB[3];
+  int M, N, K;
+  int n_planes;
+  int k_slices;
+  int m_tiles, n_tiles;
+  Epi epi;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, 128B swizzle, version 1 (sm_100).
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// product p of the plane expansion -> (a_plane, b_plane); ordered small-to-large magnitude last
+__device__ __forceinline__ void product_planes(int n_planes, int p, int& pa, int& pb) {
+  // n_planes==1: (0,0); ==2: (0,1),(1,0),(0,0); ==3: (0,2),(2,0),(1,1),(0,1),(1,0),(0,0)
+  const int np = (n_planes == 1) ? 1 : (n_planes == 2 ? 3 : 6);
+  const int q = np - 1 - p;  // q=0 is (0,0)
+  const int ta[6] = {0, 1, 0, 1, 2, 0};
+  const int tb[6] = {0, 0, 1, 1, 0, 2};
+  pa = ta[q];
+  pb = tb[q];
+}
+
+template <int BN, int MN_MAJOR>
+__global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int A_TILE = BM * BK * 2;
+  constexpr int B_TILE = BN * BK * 2;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages (power of 2)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int P = p.n_planes;
+  const int stage_bytes = P * (A_TILE + B_TILE);
+  int stages = STAGE_BUDGET / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
+  // bars[0..8) full, [8..16) empty, [16..18) tmem_full, [18..20) tmem_empty; then tmem ptr
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8);
+  const uint32_t bar_tfull = smem_u32(bars + 16), bar_tempty = smem_u32(bars + 18);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P; ++i) {
+      tma_prefetch_desc(&p.tmA[i]);
+      tma_prefetch_desc(&p.tmB[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, N_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.k_slices - 1) / p.k_slices;
+  const int n_items = p.m_tiles * p.n_tiles * p.k_slices;
+  const int n_prod = (P == 1) ? 1 : (P == 2 ? 3 : 6);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item % p.k_slices;
+        const int t = item / p.k_slices;
+        const int n0 = (t % p.n_tiles) * BN, m0 = (t / p.n_tiles) * BM;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + P * A_TILE;
+          for (int pl = 0; pl < P; ++pl) {
+            if (MN_MAJOR == 0) {
+              tma_load_2d(sa + pl * A_TILE, &p.tmA[pl], bar_full + 8 * s, kb * BK, m0);
+              tma_load_2d(sb + pl * B_TILE, &p.tmB[pl], bar_full + 8 * s, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int sl = 0; sl < BM / 64; ++sl)
+                tma_load_2d(sa + pl * A_TILE + sl * (64 * BK * 2), &p.tmA[pl], bar_full + 8 * s,
+                            m0 + 64 * sl, kb * BK);
+#pragma unroll
+              for (int sl = 0; sl < BN / 64; ++sl)
+                tma_load_2d(sb + pl * B_TILE + sl * (64 * BK * 2), &p.tmB[pl], bar_full + 8 * s,
+                            n0 + 64 * sl, kb * BK);
+            }
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR);
+      // K-major: SBO = 8 rows * 128 B; MN-major: LBO = stride between 64-wide MN slabs, SBO = 8 k-rows
+      constexpr uint32_t LBO = MN_MAJOR ? (64 * BK * 2) : 16;
+      constexpr uint32_t SBO = 1024;
+      constexpr uint32_t KSTEP = MN_MAJOR ? (16 * 128) : 32;  // bytes per UMMA_K=16
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item % p.k_slices;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t first = 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + P * A_TILE;
+          for (int pr = 0; pr < n_prod; ++pr) {
+            int pa, pb;
+            product_planes(P, pr, pa, pb);
+            const uint64_t da = make_sdesc(sa + pa * A_TILE, LBO, SBO);
+            const uint64_t db = make_sdesc(sb + pb * B_TILE, LBO, SBO);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        if (kb1 > kb0) {
+          umma_commit(bar_tfull + 8 * acc);
+        } else {
+          // empty slice: nothing accumulated; still hand the (stale) stage over so roles stay in step
+          umma_commit(bar_tfull + 8 * acc);
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;                // column interleave among warps of the same quarter
+    constexpr int CH_PER = N_EPI_WARPS / 4;   // warps per quarter
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item % p.k_slices;
+      const int t = item / p.k_slices;
+      const int n0 = (t % p.n_tiles) * BN, m0 = (t / p.n_tiles) * BM;
+      const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      if (kb1 > kb0) {
+        for (int c = chalf; c < BN / 32; c += CH_PER) {
+          const int nc = n0 + c * 32;
+          if (nc >= p.N) break;               // warp-uniform
+          float v[32];
+          tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+          if (m < p.M) epi_apply<32>(p.epi, m, nc, v, p.N);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point fetched at run time: no link-time libcuda)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld &&
+           box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ (size_t)k.inner; h = h * 1000003u ^ (size_t)k.outer;
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)(k.box_inner * 1024 + k.box_outer);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+
+// 2-D bf16 tensor map: inner (contiguous) x outer rows, row pitch ld elements, 128B swizzle.
+static int make_map(CUtensorMap* out, const bf16* ptr, long long inner, long long outer, long long ld,
+                    int box_inner, int box_outer) {
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return NRW_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  NRW_CHECK(enc != nullptr, NRW_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  NRW_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0, NRW_ERR_ARG,
+            "TMA operand must be 16B aligned with ld %% 8 == 0 (ptr=%p ld=%lld)", (const void*)ptr, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRW_CHECK(r == CUDA_SUCCESS, NRW_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld",
+            (int)r, inner, outer, ld);
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  if (g_map_cache.size() > 65536) g_map_cache.clear();
+  g_map_cache.emplace(key, *out);
+  return NRW_OK;
+}
+
+static long long g_tc_launches = 0;
+long long gemm_tc_launch_count() { return g_tc_launches; }
+
+template <int BN, int MN>
+static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = p.m_tiles * p.n_tiles * p.k_slices;
+  const int grid = items < n_sm ? items : n_sm;
+  gemm_tc_kernel<BN, MN><<<grid, N_THREADS, SMEM_BYTES, stream>>>(p);
+  NRW_LAUNCH_OK();
+  ++g_tc_launches;
+  return NRW_OK;
+}
+
+int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
+  NRW_CHECK(g.M > 0 && g.N > 0 && g.K > 0, NRW_ERR_ARG, "gemm_tc: empty problem %d %d %d", g.M, g.N, g.K);
+  NRW_CHECK(g.n_planes >= 1 && g.n_planes <= 3, NRW_ERR_ARG, "gemm_tc: n_planes=%d", g.n_planes);
+  NRW_CHECK(g.k_slices == 1 || g.epi.atomic, NRW_ERR_ARG, "gemm_tc: split-K needs an atomic epilogue");
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    NRW_CUDA_OK(cudaGetDevice(&dev));
+    NRW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int BN;
+  if (g.N <= 64) BN = 64;
+  else if (g.N <= 128 || g.n_planes >= 2) BN = 128;
+  else BN = 256;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K; p.n_planes = g.n_planes; p.k_slices = g.k_slices;
+  p.m_tiles = cdiv(g.M, BM); p.n_tiles = cdiv(g.N, BN);
+  p.epi = g.epi;
+  for (int pl = 0; pl < g.n_planes; ++pl) {
+    if (!g.mn_major) {
+      NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);
+      NRW_TRY(make_map(&p.tmA[pl], g.A.plane(pl), g.K, g.M, g.A.ld, BK, BM));
+      NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.K, g.N, g.B.ld, BK, BN));
+    } else {
+      NRW_TRY(make_map(&p.tmA[pl], g.A.plane(pl), g.M, g.K, g.A.ld, 64, BK));
+      NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.N, g.K, g.B.ld, 64, BK));
+    }
+  }
+  if (!g.mn_major) {
+    if (BN == 64) return launch<64, 0>(p, n_sm, stream);
+    if (BN == 128) return launch<128, 0>(p, n_sm, stream);
+    return launch<256, 0>(p, n_sm, stream);
+  } else {
+    if (BN == 64) return launch<64, 1>(p, n_sm, stream);
+    if (BN == 128) return launch<128, 1>(p, n_sm, stream);
+    return launch<256, 1>(p, n_sm, stream);
+  }
+}
+
+}  // namespace nrw

@@ -1,0 +1,12 @@
+// K1a: ray / sparse-octree intersection (octree.cu)
+#pragma once
+#include "common.cuh"
+
+namespace nrw {
+int octree_near_far(const uint8_t* octree, const int32_t* prefix, const int32_t* pyramid_host, int level,
+                    const float* rays_o, const float* rays_d, int R, const float scene_origin[3], float scale,
+                    float* near, float* far, int32_t* pid, int32_t* count, cudaStream_t s);
+int octree_hits(const uint8_t* octree, const int32_t* prefix, const int32_t* pyramid_host, int level,
+                const float* rays_o, const float* rays_d, int R, const float scene_origin[3], float scale,
+                const int64_t* offsets, int32_t* ray_index, int32_t* point_index, float* depth, cudaStream_t s);
+}  // namespace nrw

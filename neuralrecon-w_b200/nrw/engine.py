@@ -1,0 +1,270 @@
+"""Host-side engine: owns the flat parameter buffer, the libnrw context and its workspace, and the
+autograd bridge for the fused render path.  PyTorch is plumbing here (device memory, streams,
+autograd routing); all arithmetic of the hot path happens inside libnrw.so."""
+import ctypes as C
+import os
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import NrwError, RenderCfg, RenderGrads, RenderIO, SamplerCfg, check, ptr, stream_ptr
+
+PRECISIONS = {"bf16": 1, "bf16x3": 2, "bf16x6": 3}
+
+
+def default_precision():
+    return os.environ.get("NRW_PRECISION", "bf16x3")
+
+
+def default_backend():
+    return _lib.NRW_GEMM_SIMT if os.environ.get("NRW_GEMM", "tcgen05").lower() == "simt" else _lib.NRW_GEMM_TCGEN05
+
+
+class Engine:
+    """One per (neuconw, nerf) pair and device.  Parameters of both modules become views of one flat
+    fp32 buffer laid out by nrw_param_table (include/nrw.h), so the backward kernels write one flat
+    gradient buffer that a single NCCL all-reduce can reduce."""
+
+    def __init__(self, neuconw=None, nerf=None, n_vocab=0, n_a=48, precision=None, backend=None, chunk_rows=None):
+        self.L = _lib.lib()
+        self.neuconw = neuconw
+        self.nerf = nerf
+        self.n_vocab = int(n_vocab)
+        self.n_a = int(n_a)
+        self.precision = precision or default_precision()
+        if self.precision not in PRECISIONS:
+            raise NrwError(f"unknown precision {self.precision!r}; choose from {sorted(PRECISIONS)}")
+        self.n_planes = PRECISIONS[self.precision]
+        self.backend = default_backend() if backend is None else backend
+        self.chunk_rows = int(chunk_rows or os.environ.get("NRW_CHUNK_ROWS", 32768))
+        self.table, self.total = _lib.param_table(self.n_vocab, self.n_a)
+        self.index = {name: (shape, off, numel) for name, shape, off, numel in self.table}
+        self.ctx = C.c_void_p()
+        check(self.L.nrw_ctx_create(C.byref(self.ctx), self.n_planes, self.backend, self.n_vocab, self.n_a),
+              "nrw_ctx_create")
+        self.flat = None
+        self.packed = None
+        self.workspace = None
+        self.bound = (0, 0, 0, 0)
+        self.last_flat_grad = None
+        for m in (neuconw, nerf):
+            if m is not None:
+                m._nrw_engine = weakref.ref(self)
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                self.L.nrw_ctx_destroy(self.ctx)
+        except Exception:
+            pass
+
+    # ---- parameters -------------------------------------------------------------------------
+    def named_params(self):
+        out = []
+        for prefix, mod in (("neuconw.", self.neuconw), ("nerf.", self.nerf)):
+            if mod is None:
+                continue
+            for k, p in mod.named_parameters():
+                out.append((prefix + k, p))
+        return out
+
+    def flatten(self, device):
+        """(Re)establish that every parameter is a view of self.flat; cheap when already true."""
+        named = self.named_params()
+        if self.flat is not None and self.flat.device == device:
+            base = self.flat.data_ptr()
+            if all(p.data_ptr() == base + self.index[k][1] * 4 and p.device == device for k, p in named):
+                return named
+        flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        for k, p in named:
+            if k not in self.index:
+                raise NrwError(f"parameter {k} is not part of the supported architecture")
+            shape, off, numel = self.index[k]
+            if tuple(p.shape) != tuple(shape):
+                raise NrwError(f"parameter {k} has shape {tuple(p.shape)}, the CUDA path needs {shape}")
+            view = flat[off:off + numel].view(shape)
+            view.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = view
+        self.flat = flat
+        return named
+
+    # ---- context / workspace ----------------------------------------------------------------
+    def ensure(self, device, max_rays, max_T, with_backward):
+        max_rays = max(int(max_rays), 1)
+        max_T = max(int(max_T), 2)
+        chunk = max(self.chunk_rows, ((max_T + 127) // 128) * 128)
+        b = self.bound
+        if (self.workspace is not None and self.workspace.device == device and b[0] >= max_rays and b[1] >= max_T
+                and b[2] >= int(with_backward) and b[3] == chunk):
+            return
+        max_rays = max(max_rays, b[0])
+        max_T = max(max_T, b[1])
+        with_backward = max(int(with_backward), b[2])
+        with torch.cuda.device(device):
+            if self.packed is None or self.packed.device != device:
+                nb = self.L.nrw_packed_bytes(self.ctx)
+                self.packed = torch.empty(nb + 1024, dtype=torch.uint8, device=device)
+            wb = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T)
+            self.workspace = None
+            self.workspace = torch.empty(wb + 2048, dtype=torch.uint8, device=device)
+            pk = (self.packed.data_ptr() + 1023) // 1024 * 1024
+            ws = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+            check(self.L.nrw_ctx_bind(self.ctx, C.c_void_p(pk), self.packed.numel() - (pk - self.packed.data_ptr()),
+                                      C.c_void_p(ws), self.workspace.numel() - (ws - self.workspace.data_ptr()),
+                                      chunk, with_backward, max_rays, max_T, stream_ptr()), "nrw_ctx_bind")
+        self.bound = (max_rays, max_T, with_backward, chunk)
+
+    def pack(self, device):
+        named = self.flatten(device)
+        check(self.L.nrw_pack_weights(self.ctx, ptr(self.flat), stream_ptr()), "nrw_pack_weights")
+        return named
+
+    # ---- operations -------------------------------------------------------------------------
+    def sdf(self, pts):
+        """SDF values for pts [n,3] -> [n] (NeuconWRenderer.sdf, rendering/renderer.py:947-949)."""
+        pts = pts.detach().reshape(-1, 3).contiguous().float()
+        dev = pts.device
+        self.ensure(dev, 1, 2, 0)
+        self.pack(dev)
+        out = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
+        check(self.L.nrw_sdf_query(self.ctx, ptr(pts), pts.shape[0], ptr(out), stream_ptr()), "nrw_sdf_query")
+        return out
+
+    def neuconw_forward(self, pts, dirs, a, want_rgb=True):
+        pts = pts.detach().reshape(-1, 3).contiguous().float()
+        n, dev = pts.shape[0], pts.device
+        self.ensure(dev, 1, 2, 0)
+        self.pack(dev)
+        sdf = torch.empty(n, dtype=torch.float32, device=dev)
+        nrm = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_rgb else None
+        dirs_c = dirs.detach().reshape(-1, 3).contiguous().float() if want_rgb else None
+        a_c = a.detach().reshape(n, -1).contiguous().float() if want_rgb else None
+        check(self.L.nrw_neuconw_forward(self.ctx, ptr(pts), ptr(dirs_c), ptr(a_c), n, ptr(rgb), ptr(sdf), ptr(nrm),
+                                         stream_ptr()), "nrw_neuconw_forward")
+        return rgb, sdf, nrm
+
+    def nerf_forward(self, pts4, dirs, a):
+        pts4 = pts4.detach().reshape(-1, 4).contiguous().float()
+        n, dev = pts4.shape[0], pts4.device
+        self.ensure(dev, 1, 2, 0)
+        self.pack(dev)
+        dens = torch.empty(n, 1, dtype=torch.float32, device=dev)
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        check(self.L.nrw_nerf_forward(self.ctx, ptr(pts4), ptr(dirs.detach().reshape(-1, 3).contiguous().float()),
+                                      ptr(a.detach().reshape(n, -1).contiguous().float()), n, ptr(dens), ptr(rgb),
+                                      stream_ptr()), "nrw_nerf_forward")
+        return dens, rgb
+
+    def sample(self, scfg, o, d, near, far, s_near=None, s_far=None, u_ray=None, u_out=None, trace=False):
+        R, dev = o.shape[0], o.device
+        fine = s_near is not None
+        S = self.L.nrw_samples_per_ray(C.byref(scfg), int(fine))
+        self.ensure(dev, R, S + scfg.n_outside, self.bound[2])
+        self.pack(dev)
+        z = torch.empty(R, S, dtype=torch.float32, device=dev)
+        zo = torch.empty(R, max(scfg.n_outside, 0), dtype=torch.float32, device=dev)
+        sd = torch.empty(R, dtype=torch.float32, device=dev)
+        ti = to = None
+        if trace and scfg.n_importance > 0:
+            k = scfg.up_sample_steps
+            n_new = scfg.n_importance // k
+            ti = torch.zeros(k * R * n_new, dtype=torch.int32, device=dev)
+            tot = sum(R * (scfg.n_samples + (i + 1) * n_new) for i in range(k))
+            to = torch.zeros(tot, dtype=torch.int32, device=dev)
+        c = lambda t: None if t is None else t.detach().reshape(-1).contiguous().float()
+        args = [c(o.reshape(-1)), c(d.reshape(-1)), c(near), c(far), c(s_near), c(s_far), c(u_ray), c(u_out)]
+        check(self.L.nrw_sample(self.ctx, C.byref(scfg), R, *[ptr(t) for t in args], ptr(z), ptr(zo), ptr(sd),
+                                ptr(ti), ptr(to), stream_ptr()), "nrw_sample")
+        return z, zo, sd, ti, to
+
+    def render(self, rcfg, o, d, z_vals, z_out, sample_dist, a_emb, inv_s):
+        """Differentiable fused render core.  Returns a dict of tensors (see _RenderFn)."""
+        dev = o.device
+        need_grad = torch.is_grad_enabled()
+        T = rcfg.S + rcfg.n_outside
+        self.ensure(dev, rcfg.R, T, int(need_grad))
+        named = self.pack(dev)
+        params = [p for _, p in named]
+        outs = _RenderFn.apply(self, rcfg, o, d, z_vals, z_out, sample_dist, a_emb, inv_s, *params)
+        keys = ["color", "color_sphere", "color_bg", "cdf", "gradients", "weights", "weights_sum", "inside_sphere",
+                "depth", "normals", "gradient_error"]
+        return dict(zip(keys, outs))
+
+
+def _io_struct(tensors):
+    io = RenderIO()
+    for k in _lib._IO_FIELDS:
+        setattr(io, k, ptr(tensors.get(k)))
+    return io
+
+
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, rcfg, o, d, z_vals, z_out, sample_dist, a_emb, inv_s, *params):
+        dev = o.device
+        R, S, n_o = rcfg.R, rcfg.S, rcfg.n_outside
+        T = S + n_o
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        t = dict(o=o.contiguous(), d=d.contiguous(), z_vals=z_vals.contiguous(), z_out=z_out.contiguous(),
+                 sample_dist=sample_dist.contiguous(), a_emb=a_emb.detach().contiguous(),
+                 inv_s=inv_s.detach().reshape(1).contiguous().float(),
+                 color=f(R, 3), color_sphere=f(R, 3), color_bg=f(R, 3), cdf=f(R, S), gradients=f(R, S, 3),
+                 weights=f(R, T), weights_sum=f(R), inside_sphere=f(R, S), depth=f(R), normals=f(R, 3),
+                 gradient_error=f(1), sv_sdf=f(R, S), sv_rgb=f(R, S, 3), sv_bg_alpha=f(R, T), sv_bg_rgb=f(R, T, 3),
+                 sv_z_feed=f(R, T), sv_relax_sum=f(1))
+        io = _io_struct(t)
+        check(eng.L.nrw_render_forward(eng.ctx, C.byref(rcfg), C.byref(io), stream_ptr()), "nrw_render_forward")
+        ctx.eng, ctx.rcfg, ctx.t = eng, rcfg, t
+        ctx.inv_s_shape = inv_s.shape
+        ctx.n_params = len(params)
+        ctx.param_meta = [(p.shape, eng.index[k][1], eng.index[k][2]) for (k, _), p in zip(eng.named_params(), params)]
+        ctx.mark_non_differentiable(t["inside_sphere"])
+        ctx.set_materialize_grads(False)
+        return (t["color"], t["color_sphere"], t["color_bg"], t["cdf"], t["gradients"], t["weights"],
+                t["weights_sum"], t["inside_sphere"], t["depth"], t["normals"], t["gradient_error"])
+
+    @staticmethod
+    def backward(ctx, g_color, g_cs, g_cb, g_cdf, g_grad, g_w, g_ws, g_inside, g_depth, g_normals, g_ge):
+        eng, rcfg, t = ctx.eng, ctx.rcfg, ctx.t
+        dev = t["o"].device
+        if eng.bound[2] < 1:
+            raise NrwError("render was run under no_grad; cannot backpropagate through it")
+        c = lambda g: None if g is None else g.contiguous().float()
+        gs = dict(g_color=c(g_color), g_color_sphere=c(g_cs), g_color_bg=c(g_cb), g_cdf=c(g_cdf), g_gradients=c(g_grad),
+                  g_weights=c(g_w), g_weights_sum=c(g_ws), g_depth=c(g_depth), g_normals=c(g_normals),
+                  g_gradient_error=c(g_ge))
+        flat_grad = torch.zeros(eng.total, dtype=torch.float32, device=dev)
+        g_a = torch.empty(rcfg.R, eng.n_a, dtype=torch.float32, device=dev)
+        g_invs = torch.zeros(1, dtype=torch.float32, device=dev)
+        gr = RenderGrads()
+        for k, v in gs.items():
+            setattr(gr, k, ptr(v))
+        gr.grad_params, gr.grad_a_emb, gr.grad_inv_s = ptr(flat_grad), ptr(g_a), ptr(g_invs)
+        io = _io_struct(t)
+        check(eng.L.nrw_render_backward(eng.ctx, C.byref(rcfg), C.byref(io), C.byref(gr), stream_ptr()),
+              "nrw_render_backward")
+        eng.last_flat_grad = flat_grad
+        pgrads = [flat_grad[off:off + numel].view(shape) for shape, off, numel in ctx.param_meta]
+        return (None, None, None, None, None, None, None, g_a, g_invs.reshape(ctx.inv_s_shape), *pgrads)
+
+
+def make_sampler_cfg(n_samples, n_importance, up_sample_steps, n_outside, s_val_base, boundary_samples, perturb):
+    return SamplerCfg(int(n_samples), int(n_importance), int(up_sample_steps), int(n_outside), int(s_val_base),
+                      int(boundary_samples or 0), int(bool(perturb)))
+
+
+def make_render_cfg(R, S, n_outside, cos_anneal_ratio, background_rgb, trim_sphere):
+    cfg = RenderCfg()
+    cfg.R, cfg.S, cfg.n_outside = int(R), int(S), int(n_outside)
+    cfg.cos_anneal_ratio = float(cos_anneal_ratio)
+    # device pointer; the caller keeps `background_rgb` alive (it is stashed on the cfg object)
+    cfg._bg_keepalive = None
+    if background_rgb is not None:
+        cfg._bg_keepalive = background_rgb.detach().reshape(-1)[:3].contiguous().float()
+        cfg.background_rgb = cfg._bg_keepalive.data_ptr()
+    else:
+        cfg.background_rgb = None
+    cfg.trim_sphere = int(bool(trim_sphere))
+    return cfg
