@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the NeuralRecon-W per-ray training hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl nrw|reference] [--precision bf16x3|bf16|bf16x6]
+
+A "step" = one full training step over one batch of 8192 synthetic posed-camera rays x 128 samples
+(BASELINE config C2 "brandenburg_gate config, 8192 rays x 128 samples"): voxel-guided hierarchical
+sampling -> background NeRF -> SDF value/normal -> colour net -> NeuS compositing -> loss -> backward
+(hand-derived second order) -> [NCCL all-reduce] -> clip(0.99) -> Adam.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "neuralrecon-w_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+# algorithmic FLOP per sample (2*MAC, forward) of the three MLPs (SURVEY.md 8 / BASELINE.md 3)
+F_SDF, F_COL, F_NERF = 4195328, 1170688, 1318912
+WORKLOADS = {
+    "C2": dict(n_samples=64, n_importance=64, up_sample_steps=4, n_outside=4, rays=8192,
+               name="brandenburg_gate config, synthetic ray cache, 8192 rays x 128 samples (64 coarse + 64 importance, 4 up-sample rounds, 4 outside)"),
+    "C1": dict(n_samples=64, n_importance=16, up_sample_steps=2, n_outside=4, rays=1024,
+               name="400x400 synthetic pinhole camera, 1024-ray batch, 64 coarse + 16 importance samples"),
+}
+
+
+def flop_per_ray(w):
+    """W_ray = F*[(n_s + (k-1) n_i/k) + 6 S] + 3 C S + 3 N T  (SURVEY.md 8d)."""
+    k = w["up_sample_steps"]
+    n_new = w["n_importance"] // k
+    S = w["n_samples"] + k * n_new
+    T = S + w["n_outside"]
+    evals = w["n_samples"] + (k - 1) * n_new
+    return F_SDF * (evals + 6 * S) + 3 * F_COL * S + 3 * F_NERF * T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1409.5), d.get("hbm_gbs", 6576.7), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference(workload, n_rays_cpu, steps, warmup, threads):
+    """The reference's own PyTorch CPU path, restated in oracle/neuconw_port.py (pinned to the unmodified
+    reference by tests/golden), timed on the host cores: render + loss + backward on a bounded ray sample."""
+    from oracle import neuconw_port as port
+    from oracle import synth
+
+    torch.set_num_threads(threads)
+    w = WORKLOADS[workload]
+    cfg = synth.PathConfig(n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=w["up_sample_steps"],
+                           n_outside=w["n_outside"], perturb=1.0)
+    P = synth.make_params(seed=0)
+    batch = synth.make_rays(n_rays_cpu, cfg, seed=1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        port.train_step(P, cfg, batch, perturb_overwrite=-1)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return n_rays_cpu / dt, dt
+
+
+def torch_gpu_reference(workload, n_rays, steps, device):
+    """Same restated reference ops on CUDA tensors (= what the reference executes on a GPU: stock
+    torch.nn / cuBLAS fp32), on a bounded ray sample; the '>= 4x' denominator of BASELINE.json."""
+    from oracle import neuconw_port as port
+    from oracle import synth
+
+    w = WORKLOADS[workload]
+    cfg = synth.PathConfig(n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=w["up_sample_steps"],
+                           n_outside=w["n_outside"], perturb=1.0)
+    P = {k: v.to(device) for k, v in synth.make_params(seed=0).items()}
+    batch = {k: v.to(device) for k, v in synth.make_rays(n_rays, cfg, seed=1).items()}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(2):
+        port.train_step(P, cfg, batch, perturb_overwrite=-1)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        port.train_step(P, cfg, batch, perturb_overwrite=-1)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    return n_rays / (ms * 1e-3), ms
+
+
+def gemm_microbench(device, n_planes):
+    """Dominant kernel alone: one 512x512 SDF layer over 65536 samples (tcgen05 GEMM + softplus epilogue)."""
+    import ctypes as C
+    from nrw import _lib
+
+    L = _lib.lib()
+    M, N, K = 65536, 512, 512
+    A = torch.randn(M, K, device=device)
+    B = torch.randn(N, K, device=device) / 22.0
+    bias = torch.zeros(N, device=device)
+    D = torch.empty(M, N, device=device)
+    scratch = torch.empty(L.nrw_gemm_test_scratch_bytes(M, N, K) + 1024, dtype=torch.uint8, device=device)
+    sp = (scratch.data_ptr() + 1023) // 1024 * 1024
+    # flush-sized filler so operands do not sit in L2 between iterations
+    filler = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    ts = []
+    for it in range(8):
+        filler.zero_()
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        # includes the plane-split pre-pass; time the GEMM by differencing with a split-only call is overkill:
+        # the split kernels are ~10% of this call, reported as-is (conservative)
+        t0.record()
+        _lib.check(L.nrw_gemm_test(0, n_planes, 0, 1, M, N, K, _lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), 1, _lib.ptr(D),
+                                   C.c_void_p(sp), _lib.stream_ptr()), "gemm_test")
+        t1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(t0.elapsed_time(t1))
+    ms = sorted(ts)[len(ts) // 2]
+    return 2.0 * M * N * K / (ms * 1e-3) / 1e12, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nrw", choices=["nrw", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NRW_PRECISION", "bf16x3"))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rays", type=int, default=0)
+    ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 32768)))
+    ap.add_argument("--cpu_rays", type=int, default=32)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_torch_gpu_ref", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.rays:
+        w["rays"] = args.rays
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    k = w["up_sample_steps"]
+    S = w["n_samples"] + k * (w["n_importance"] // k)
+    config = {"workload": w["name"], "rays_per_gpu": w["rays"], "samples_per_ray": S, "outside_samples": w["n_outside"],
+              "l2": "per-step working set (>= 4 GB of chunk activations) far exceeds the 126 MB L2; no flush needed",
+              "parallelism": f"dp{world}" if world > 1 else "single"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        rps, dt = cpu_reference(args.workload, args.cpu_rays, max(1, min(args.steps, 3)), 1 if args.warmup else 0, threads)
+        line = {"impl": "reference", "metric": "training rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+                "steps": max(1, min(args.steps, 3)), "warmup": 1 if args.warmup else 0, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                 "sample": f"{args.cpu_rays} rays x {S} samples per step (render+loss+backward, torch CPU fp32, oracle/neuconw_port.py)"},
+                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ product arm
+    assert torch.cuda.is_available(), "bench.py --impl nrw needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from nrw import _lib
+    from nrw.synthetic import make_ray_batch
+    from nrw.train import TrainSystem
+
+    sysm = TrainSystem(device, n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=k,
+                       n_outside=w["n_outside"], precision=args.precision, chunk_rows=args.chunk_rows,
+                       batch_size=w["rays"], world_size=world, seed=66)
+    R = w["rays"]
+    host = make_ray_batch(R, seed=1 + rank, pin=True)          # pinned host copy (e2e arm)
+    dev_batch = {kk: v.to(device, non_blocking=True) for kk, v in host.items()}
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, from_host):
+        last = None
+        for _ in range(n):
+            b = {kk: v.to(device, non_blocking=True) for kk, v in host.items()} if from_host else dev_batch
+            loss = sysm.training_step(b)
+            last = loss.item() if from_host else loss      # e2e: device->host read of the step's loss
+        return last
+
+    run(max(args.warmup, 3), False)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = L.nrw_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    loss = run(args.steps, False)
+    e1.record()
+    barrier()
+    launches = (L.nrw_launch_count() - l0) // max(args.steps, 1)
+    ms = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    # e2e: host buffers, H2D of the batch + D2H of the loss inside the timed region
+    run(1, True)
+    barrier()
+    e0.record()
+    run(args.steps, True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    flops_step = flop_per_ray(w) * R
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved_tf = flops_step / (ms * 1e-3) / 1e12
+    line = {"metric": "training rays/sec", "value": R * world / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16 (3-product split, fp32 accumulate)",
+                                                            "bf16x6": "bf16 (6-product split, fp32 accumulate)"}[args.precision],
+            "data": "synthetic", "config": config, "precision_mode": args.precision, "loss": float(loss),
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "kernel": "gemm_tc_kernel (all dense layers of the step; algorithmic FLOP = 4.66 GFLOP/ray x rays)",
+                         "algorithmic_tflop_per_step": flops_step / 1e12}}
+    if world == 1:
+        try:
+            tf, gms = gemm_microbench(device, {"bf16": 1, "bf16x3": 2, "bf16x6": 3}[args.precision])
+            line["roofline"]["gemm_kernel"] = {"shape": "M=65536 N=512 K=512 (one SDF layer + softplus epilogue)",
+                                               "achieved": tf, "unit": "TFLOP/s (algorithmic 2MNK)", "ms": gms,
+                                               "frac": tf / peak_tf}
+        except Exception as e:  # noqa
+            line["roofline"]["gemm_kernel"] = {"error": str(e)[:200]}
+        if not args.no_torch_gpu_ref:
+            try:
+                rps, rms = torch_gpu_reference(args.workload, 1024, 3, device)
+                line["reference_torch_gpu"] = {"value": rps, "unit": "rays/s", "ms_per_step": rms,
+                                               "sample": f"1024 rays x {S} samples, stock torch fp32 ops of the reference path on this GPU"}
+            except Exception as e:  # noqa
+                line["reference_torch_gpu"] = {"error": str(e)[:200]}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rps, dt = cpu_reference(args.workload, args.cpu_rays, 2, 1, threads)
+            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_rays} rays x {S} samples per step, 2 timed steps (render+loss+backward, torch CPU fp32)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

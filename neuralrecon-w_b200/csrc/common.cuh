@@ -38,7 +38,12 @@ void set_last_error(const char* fmt, ...);
     int _s = (expr);                                                                   \
     if (_s != NRW_OK) return _s;                                                       \
   } while (0)
-#define NRW_LAUNCH_OK() NRW_CUDA_OK(cudaGetLastError())
+extern long long g_kernel_launches;  // every kernel launch of the library bumps this (pack.cu)
+#define NRW_LAUNCH_OK()                \
+  do {                                 \
+    ++::nrw::g_kernel_launches;        \
+    NRW_CUDA_OK(cudaGetLastError());   \
+  } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }

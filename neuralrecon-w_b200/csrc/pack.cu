@@ -6,6 +6,7 @@
 
 namespace nrw {
 
+long long g_kernel_launches = 0;
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
   va_list ap;

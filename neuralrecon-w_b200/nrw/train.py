@@ -1,0 +1,98 @@
+"""Minimal training harness around the drop-in classes: the pieces of NeuconWSystem / train.py the hot
+path needs (lightning_modules/neuconw_system.py:61-176,337-360; losses.py:21-43; utils/__init__.py:23-41;
+train.py:21-25,61), without PyTorch-Lightning.  One process per GPU; data-parallel ranks reduce the
+flat gradient buffer with one NCCL all-reduce."""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .models import NeRF, NeuconW
+from .renderer import LABEL_IDS, NeuconWRenderer
+
+SDF_CONFIG = dict(d_in=3, d_out=513, d_hidden=512, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1,
+                  geometric_init=True, weight_norm=True, inside_outside=False)
+COLOR_CONFIG = dict(d_in=9, d_feature=512, mode="idr", d_out=3, d_hidden=256, n_layers=4, head_channels=128,
+                    static_head_layers=2, weight_norm=True, multires_view=4)
+
+
+class NeuconWLoss(torch.nn.Module):
+    """losses.py:21-43 (masks=None branch; floor term off)."""
+
+    def __init__(self, coef=1.0, igr_weight=0.1, mask_weight=0.1, depth_weight=0.1, use_mask=True, use_depth=True):
+        super().__init__()
+        self.coef, self.igr_weight, self.mask_weight, self.depth_weight = coef, igr_weight, mask_weight, depth_weight
+        self.use_mask, self.use_depth = use_mask, use_depth
+
+    def forward(self, inputs, targets):
+        mask_sum = float(targets.shape[0]) + 1e-5
+        ret = {"color_loss": (inputs["color"] - targets).abs().sum() / mask_sum,
+               "normal_loss": self.igr_weight * inputs["gradient_error"].mean()}
+        if self.use_mask:
+            ret["mask_error"] = self.mask_weight * inputs["mask_error"].mean()
+        if self.use_depth:
+            ret["sfm_depth_loss"] = self.depth_weight * inputs["sfm_depth_loss"].mean()
+        return {k: self.coef * v for k, v in ret.items()}
+
+
+class TrainSystem:
+    """embedding_a + neuconw + nerf + renderer + loss + Adam, i.e. what NeuconWSystem owns."""
+
+    def __init__(self, device, n_samples=64, n_importance=64, up_sample_steps=4, n_outside=4, s_val_base=3,
+                 n_vocab=5000, n_a=48, origin=(0.0, 0.0, 0.0), radius=1.0, precision=None, chunk_rows=None,
+                 batch_size=8192, world_size=1, canonical_lr=1e-4, canonical_bs=4096, anneal_end=50000,
+                 igr_weight=0.0001, mask_weight=0.1, depth_weight=0.1, seed=66):
+        torch.manual_seed(seed)
+        self.device = device
+        self.embedding_a = torch.nn.Embedding(n_vocab, n_a).to(device)
+        self.neuconw = NeuconW(SDF_CONFIG, COLOR_CONFIG, dict(init_val=0.3), in_channels_a=n_a, encode_a=True).to(device)
+        self.nerf = NeRF(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, output_ch=4, skips=[4],
+                         encode_appearance=True, in_channels_a=n_a, in_channels_dir=27, use_viewdirs=True).to(device)
+        self.renderer = NeuconWRenderer(
+            nerf=self.nerf, neuconw=self.neuconw, embeddings={"a": self.embedding_a}, n_samples=n_samples,
+            s_val_base=s_val_base, n_importance=n_importance, n_outside=n_outside, up_sample_steps=up_sample_steps,
+            perturb=1.0, origin=list(origin), radius=radius, render_bg=True, mesh_mask_list=["sky"],
+            depth_loss=True, spc_options=dict(voxel_size=0.1, recontruct_path=None, min_track_length=0),
+            sample_range=16, boundary_samples=10, nerf_far_override=False, precision=precision, chunk_rows=chunk_rows)
+        self.loss = NeuconWLoss(igr_weight=igr_weight, mask_weight=mask_weight, depth_weight=depth_weight)
+        self.params = [p for m in (self.embedding_a, self.neuconw, self.nerf) for p in m.parameters()]
+        lr = canonical_lr * (world_size * batch_size / canonical_bs)  # train.py:21-25
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, eps=1e-7, weight_decay=0)  # utils/__init__.py:30
+        self.anneal_end = anneal_end
+        self.global_step = 0
+        self.world_size = world_size
+        self.ray_mask_ids = [LABEL_IDS[n] for n in ("person", "car", "bicycle", "minibike")]
+
+    def cos_anneal_ratio(self):
+        return 1.0 if self.anneal_end == 0 else min(1.0, self.global_step / self.anneal_end)
+
+    def forward(self, rays, ts, label):
+        """NeuconWSystem.forward (neuconw_system.py:159-176)."""
+        return self.renderer.render(rays, ts, label, background_rgb=torch.zeros([1, 3], device=rays.device),
+                                    cos_anneal_ratio=self.cos_anneal_ratio())
+
+    def training_step(self, batch):
+        """training_step + backward + DDP-mean all-reduce + clip(0.99) + Adam (neuconw_system.py:337-360,
+        train.py:61).  Returns the detached loss tensor (device)."""
+        rays, rgbs, ts, label = batch["rays"], batch["rgbs"], batch["ts"], batch["label"]
+        self.renderer.nerf_far_override = False
+        self.optimizer.zero_grad(set_to_none=True)
+        results = self.forward(rays, ts, label)
+        loss = sum(self.loss(results, rgbs).values())
+        loss.backward()
+        eng = self.renderer.engine
+        flat = eng.last_flat_grad
+        for k, p in eng.named_params():        # make every .grad a view of the flat gradient buffer
+            shape, off, numel = eng.index[k]
+            p.grad = flat[off:off + numel].view(shape)
+        if self.world_size > 1:
+            dist.all_reduce(flat)                      # one collective for neuconw + nerf (15 MB, NVLink)
+            flat.div_(self.world_size)
+            eg = self.embedding_a.weight.grad
+            if eg is not None:
+                dist.all_reduce(eg)
+                eg.div_(self.world_size)
+        torch.nn.utils.clip_grad_norm_(self.params, 0.99)
+        self.optimizer.step()
+        self.global_step += 1
+        return loss.detach()
