@@ -66,11 +66,13 @@ NRW_API long long nrw_param_total(int n_vocab, int n_a);
 NRW_API int nrw_ctx_create(nrw_ctx** out, int n_planes, int gemm_backend, int n_vocab, int n_a);
 NRW_API int nrw_ctx_destroy(nrw_ctx* ctx);
 NRW_API long long nrw_packed_bytes(const nrw_ctx* ctx);
+/* n_slots_sdf / n_slots_nerf: how many chunks keep their forward activations resident for the backward pass
+ * (>= number of chunks of a batch: no forward recompute in backward; 1: recompute, minimum memory). */
 NRW_API long long nrw_workspace_bytes(const nrw_ctx* ctx, int chunk_rows, int with_backward, int max_rays,
-                                      int max_samples_per_ray);
+                                      int max_samples_per_ray, int n_slots_sdf, int n_slots_nerf);
 NRW_API int nrw_ctx_bind(nrw_ctx* ctx, void* packed, long long packed_bytes, void* workspace,
                          long long workspace_bytes, int chunk_rows, int with_backward, int max_rays,
-                         int max_samples_per_ray, void* stream);
+                         int max_samples_per_ray, int n_slots_sdf, int n_slots_nerf, void* stream);
 /* weight-norm materialisation + bf16 plane split + transposes of every layer (replaces what
  * torch.nn.utils.weight_norm recomputes on every call, models/neuconw.py:104-105,256-257). */
 NRW_API int nrw_pack_weights(nrw_ctx* ctx, const float* params, void* stream);
@@ -203,6 +205,8 @@ NRW_API int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices,
                           const float* A, const float* B, const float* bias, int act, float* D,
                           void* scratch, void* stream);
 NRW_API long long nrw_launch_count(void);
+/* debug: per-CTA cycle attribution of the tcgen05 GEMM (u64 [SMs,8], zeroed by the caller; NULL = off) */
+NRW_API int nrw_debug_gemm_profile(void* device_buf_u64);
 
 #ifdef __cplusplus
 }

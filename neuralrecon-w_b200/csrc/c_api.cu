@@ -64,12 +64,14 @@ int nrw_ctx_destroy(nrw_ctx* ctx) {
   return NRW_OK;
 }
 long long nrw_packed_bytes(const nrw_ctx* ctx) { return ctx ? ctx->pm.total_bytes : 0; }
-long long nrw_workspace_bytes(const nrw_ctx* ctx, int chunk_rows, int with_backward, int max_rays, int max_T) {
+long long nrw_workspace_bytes(const nrw_ctx* ctx, int chunk_rows, int with_backward, int max_rays, int max_T,
+                              int n_slots_sdf, int n_slots_nerf) {
   if (!ctx) return 0;
-  return workspace_bytes(*ctx, chunk_rows, with_backward, max_rays, max_T);
+  return workspace_bytes(*ctx, chunk_rows, with_backward, max_rays, max_T, n_slots_sdf, n_slots_nerf);
 }
 int nrw_ctx_bind(nrw_ctx* ctx, void* packed, long long packed_bytes, void* workspace, long long ws_bytes,
-                 int chunk_rows, int with_backward, int max_rays, int max_T, void* stream) {
+                 int chunk_rows, int with_backward, int max_rays, int max_T, int n_slots_sdf, int n_slots_nerf,
+                 void* stream) {
   NRW_GUARD_BEGIN
   NRW_CHECK(ctx && packed && workspace, NRW_ERR_ARG, "ctx_bind: null argument");
   NRW_CHECK(packed_bytes >= ctx->pm.total_bytes, NRW_ERR_WORKSPACE, "ctx_bind: packed buffer %lld < %lld", packed_bytes,
@@ -81,7 +83,8 @@ int nrw_ctx_bind(nrw_ctx* ctx, void* packed, long long packed_bytes, void* works
   NRW_CUDA_OK(cudaMemcpyAsync(ctx->packed, ctx->pm.layers, sizeof(PackedLayer) * L_COUNT, cudaMemcpyHostToDevice, S(stream)));
   NRW_CUDA_OK(cudaStreamSynchronize(S(stream)));  // pm.layers is pageable host memory
   ctx->packed_valid = false;
-  return carve_workspace(*ctx, workspace, ws_bytes, chunk_rows, with_backward, max_rays, max_T, S(stream));
+  return carve_workspace(*ctx, workspace, ws_bytes, chunk_rows, with_backward, max_rays, max_T, n_slots_sdf,
+                         n_slots_nerf, S(stream));
   NRW_GUARD_END
 }
 int nrw_pack_weights(nrw_ctx* ctx, const float* params, void* stream) {
@@ -108,6 +111,9 @@ int nrw_neuconw_forward(nrw_ctx* ctx, const float* pts, const float* dirs, const
   NRW_GUARD_BEGIN
   NRW_CHECK(ctx && ctx->bound && ctx->packed_valid, NRW_ERR_STATE, "neuconw_forward: bind + pack first");
   nrw_ctx& c = *ctx;
+  c.fwd_cached = false;  // slot 0 is reused
+  c.use_sdf_slot(0);
+  c.use_nerf_slot(0);
   for (long long i = 0; i < n; i += c.Mc) {
     const int M = (int)((n - i) < c.Mc ? (n - i) : c.Mc);
     NRW_TRY(sdf_chunk_forward(c, M, pts + i * 3, true, rgb != nullptr, S(stream)));
@@ -127,6 +133,9 @@ int nrw_nerf_forward(nrw_ctx* ctx, const float* pts4, const float* dirs, const f
   NRW_GUARD_BEGIN
   NRW_CHECK(ctx && ctx->bound && ctx->packed_valid, NRW_ERR_STATE, "nerf_forward: bind + pack first");
   nrw_ctx& c = *ctx;
+  c.fwd_cached = false;  // slot 0 is reused
+  c.use_sdf_slot(0);
+  c.use_nerf_slot(0);
   for (long long i = 0; i < n; i += c.Mc) {
     const int M = (int)((n - i) < c.Mc ? (n - i) : c.Mc);
     NRW_TRY(nerf_chunk_forward(c, M, nullptr, dirs + i * 3, nullptr, nullptr, pts4 + i * 4, a + i * c.n_a, 1, 1, S(stream)));
@@ -242,5 +251,9 @@ int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices, int M, 
   NRW_GUARD_END
 }
 long long nrw_launch_count(void) { return g_kernel_launches; }
+int nrw_debug_gemm_profile(void* device_buf_u64_148x8) {
+  gemm_tc_set_profile_buffer(reinterpret_cast<unsigned long long*>(device_buf_u64_148x8));
+  return NRW_OK;
+}
 
 }  // extern "C"

@@ -30,34 +30,48 @@ struct Carver {
   }
 };
 
-static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, int max_T) {
+static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, int max_T, int n_slots_sdf,
+                  int n_slots_nerf) {
   const int P = c.n_planes;
   const long long M = Mc;
-  c.PTS = cv.f32(M * 3);
-  c.U0 = cv.planes(M, 64, P);
-  for (int l = 1; l <= 8; ++l) c.U[l] = cv.planes(M, 512, P);
-  for (int l = 0; l < 8; ++l) c.A[l] = cv.f32(M * 512);
-  for (int l = 0; l < 8; ++l) c.G[l] = cv.planes(M, 512, P);
-  c.Q[0] = cv.f32(M * 64);
-  for (int l = 1; l < 8; ++l) c.Q[l] = cv.f32(M * 512);
-  c.FEAT = cv.planes(M, 512, P);
-  c.c_sdf = cv.f32(M);
-  c.c_nrm = cv.f32(M * 3);
-  c.IN1 = cv.planes(M, 640, P);
-  c.H1 = cv.planes(M, 128, P);
-  c.IN2 = cv.planes(M, 192, P);
-  for (int l = 1; l <= 4; ++l) c.X[l] = cv.planes(M, 256, P);
-  c.c_rgb = cv.f32(M * 3);
-  c.IN0 = cv.planes(M, 128, P);
-  for (int l = 1; l <= 8; ++l)
-    if (l != 5) c.NH[l] = cv.planes(M, 256, P);
-  c.IN5 = cv.planes(M, 384, P);
-  c.FEATN = cv.planes(M, 384, P);
-  for (int l = 1; l <= 4; ++l) c.AP[l] = cv.planes(M, 128, P);
-  c.c_density = cv.f32(M);
-  c.c_alpha = cv.f32(M);
-  c.c_rgbbg = cv.f32(M * 3);
-  c.c_dists = cv.f32(M);
+  c.sdf_slots.assign(n_slots_sdf, FwdSdfSlot{});
+  c.nerf_slots.assign(n_slots_nerf, FwdNerfSlot{});
+  for (int i = 0; i < n_slots_sdf; ++i) {
+    FwdSdfSlot& s = c.sdf_slots[i];
+    s.PTS = cv.f32(M * 3);
+    s.U0 = cv.planes(M, 64, P);
+    for (int l = 1; l <= 8; ++l) s.U[l] = cv.planes(M, 512, P);
+    for (int l = 0; l < 8; ++l) s.A[l] = cv.f32(M * 512);
+    for (int l = 0; l < 8; ++l) s.G[l] = cv.planes(M, 512, P);
+    s.Q[0] = cv.f32(M * 64);
+    for (int l = 1; l < 8; ++l) s.Q[l] = cv.f32(M * 512);
+    s.FEAT = cv.planes(M, 512, P);
+    s.c_sdf = cv.f32(M);
+    s.c_nrm = cv.f32(M * 3);
+    s.IN1 = cv.planes(M, 640, P);
+    s.H1 = cv.planes(M, 128, P);
+    s.IN2 = cv.planes(M, 192, P);
+    for (int l = 1; l <= 4; ++l) s.X[l] = cv.planes(M, 256, P);
+    s.c_rgb = cv.f32(M * 3);
+  }
+  for (int i = 0; i < n_slots_nerf; ++i) {
+    FwdNerfSlot& s = c.nerf_slots[i];
+    s.IN0 = cv.planes(M, 128, P);
+    for (int l = 1; l <= 8; ++l)
+      if (l != 5) s.NH[l] = cv.planes(M, 256, P);
+    s.IN5 = cv.planes(M, 384, P);
+    s.FEATN = cv.planes(M, 384, P);
+    for (int l = 1; l <= 4; ++l) s.AP[l] = cv.planes(M, 128, P);
+    s.c_density = cv.f32(M);
+    s.c_alpha = cv.f32(M);
+    s.c_rgbbg = cv.f32(M * 3);
+    s.c_dists = cv.f32(M);
+  }
+  c.n_slots_sdf = n_slots_sdf;
+  c.n_slots_nerf = n_slots_nerf;
+  c.use_sdf_slot(0);
+  c.use_nerf_slot(0);
+  c.fwd_cached = false;
   c.ge_acc = cv.f32(4);
   if (with_bwd) {
     c.DQ0 = cv.planes(M, 64, P);
@@ -100,22 +114,25 @@ static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, in
   }
 }
 
-long long workspace_bytes(const nrw_ctx& c0, int chunk_rows, int with_bwd, int max_rays, int max_T) {
+long long workspace_bytes(const nrw_ctx& c0, int chunk_rows, int with_bwd, int max_rays, int max_T, int n_slots_sdf,
+                          int n_slots_nerf) {
   nrw_ctx c = c0;
   Carver cv{nullptr, 0, true};
-  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T);
+  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T, n_slots_sdf < 1 ? 1 : n_slots_sdf, n_slots_nerf < 1 ? 1 : n_slots_nerf);
   return round_up(cv.off, 1024) + 1024;
 }
 
 int carve_workspace(nrw_ctx& c, void* base, long long bytes, int chunk_rows, int with_bwd, int max_rays,
-                    int max_T, cudaStream_t s) {
+                    int max_T, int n_slots_sdf, int n_slots_nerf, cudaStream_t s) {
   NRW_CHECK(chunk_rows >= 128 && chunk_rows % 128 == 0, NRW_ERR_ARG, "chunk_rows=%d must be a multiple of 128", chunk_rows);
   NRW_CHECK((reinterpret_cast<uintptr_t>(base) & 255) == 0, NRW_ERR_ARG, "workspace must be 256B aligned");
-  const long long need = workspace_bytes(c, chunk_rows, with_bwd, max_rays, max_T);
+  if (n_slots_sdf < 1) n_slots_sdf = 1;
+  if (n_slots_nerf < 1) n_slots_nerf = 1;
+  const long long need = workspace_bytes(c, chunk_rows, with_bwd, max_rays, max_T, n_slots_sdf, n_slots_nerf);
   NRW_CHECK(bytes >= need, NRW_ERR_WORKSPACE, "workspace too small: %lld < %lld bytes", bytes, need);
   char* b = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~uintptr_t(1023));
   Carver cv{b, 0, false};
-  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T);
+  carve(c, cv, chunk_rows, with_bwd, max_rays, max_T, n_slots_sdf, n_slots_nerf);
   // zero once: padding columns / never-written tails must be finite (they meet zero weights)
   NRW_CUDA_OK(cudaMemsetAsync(b, 0, cv.off, s));
   c.Mc = chunk_rows; c.with_bwd = with_bwd; c.max_rays = max_rays; c.max_T = max_T;
@@ -400,6 +417,8 @@ int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bg
 // public operations
 // ---------------------------------------------------------------------------------------------
 int sdf_query(nrw_ctx& c, const float* pts, long long n, float* sdf, cudaStream_t s) {
+  c.fwd_cached = false;  // slot 0 is about to be overwritten
+  c.use_sdf_slot(0);
   for (long long i = 0; i < n; i += c.Mc) {
     const int M = (int)((n - i) < c.Mc ? (n - i) : c.Mc);
     NRW_TRY(sdf_chunk_forward(c, M, pts + i * 3, false, false, s));
@@ -456,12 +475,16 @@ int render_forward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& i
   NRW_CHECK(R <= c.max_rays && T <= c.max_T, NRW_ERR_WORKSPACE, "render: R=%d T=%d exceed bound workspace", R, T);
   NRW_CHECK(c.Mc >= T, NRW_ERR_WORKSPACE, "render: chunk_rows=%d smaller than one ray (%d)", c.Mc, T);
   const bool bg = cfg.n_outside > 0;
+  // keep every chunk's activations for the backward pass when the bound workspace has a slot per chunk
+  const bool cache = c.with_bwd && cdiv(R, c.Mc / S) <= c.n_slots_sdf && (!bg || cdiv(R, c.Mc / T) <= c.n_slots_nerf);
+  c.fwd_cached = false;
   if (bg) {
     NRW_TRY(launch_merge_sorted(R, S, cfg.n_outside, io.z_vals, io.z_out, io.sv_z_feed, s));
     const int rc = c.Mc / T;
-    for (int r0 = 0; r0 < R; r0 += rc) {
+    for (int r0 = 0, ci = 0; r0 < R; r0 += rc, ++ci) {
       const int nr = (R - r0) < rc ? (R - r0) : rc;
       const int M = nr * T;
+      c.use_nerf_slot(cache ? ci : 0);
       NRW_TRY(nerf_chunk_forward(c, M, io.o + r0 * 3, io.d + r0 * 3, io.sv_z_feed + (long long)r0 * T,
                                  io.sample_dist + r0, nullptr, io.a_emb + (long long)r0 * c.n_a, T, T, s));
       NRW_CUDA_OK(cudaMemcpyAsync(io.sv_bg_alpha + (long long)r0 * T, c.c_alpha, (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
@@ -469,9 +492,10 @@ int render_forward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& i
     }
   }
   const int rc = c.Mc / S;
-  for (int r0 = 0; r0 < R; r0 += rc) {
+  for (int r0 = 0, ci = 0; r0 < R; r0 += rc, ++ci) {
     const int nr = (R - r0) < rc ? (R - r0) : rc;
     const int M = nr * S;
+    c.use_sdf_slot(cache ? ci : 0);
     NRW_TRY(launch_points(io.o + r0 * 3, io.d + r0 * 3, io.z_vals + (long long)r0 * S, io.sample_dist + r0, nr, S, 1, c.PTS, s));
     NRW_TRY(sdf_chunk_forward(c, M, c.PTS, true, true, s));
     NRW_TRY(color_chunk_forward(c, M, c.PTS, io.d + r0 * 3, io.a_emb + (long long)r0 * c.n_a, S, s));
@@ -479,8 +503,11 @@ int render_forward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& i
     NRW_CUDA_OK(cudaMemcpyAsync(io.gradients + (long long)r0 * S * 3, c.c_nrm, (size_t)M * 12, cudaMemcpyDeviceToDevice, s));
     NRW_CUDA_OK(cudaMemcpyAsync(io.sv_rgb + (long long)r0 * S * 3, c.c_rgb, (size_t)M * 12, cudaMemcpyDeviceToDevice, s));
   }
-  return composite_forward(cfg, io, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
-                           bg ? io.sv_bg_rgb : nullptr, c.ge_acc, s);
+  NRW_TRY(composite_forward(cfg, io, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
+                            bg ? io.sv_bg_rgb : nullptr, c.ge_acc, s));
+  c.fwd_cached = cache;
+  c.cached_R = R; c.cached_S = S; c.cached_T = T;
+  return NRW_OK;
 }
 
 int render_backward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& io, const nrw_render_grads& g,
@@ -494,28 +521,38 @@ int render_backward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& 
   NRW_TRY(composite_backward(cfg, io, g, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
                              bg ? io.sv_bg_rgb : nullptr, c.g_dsdf, c.g_dnrm, c.g_drgb, bg ? c.g_dbga : nullptr,
                              bg ? c.g_dbgc : nullptr, g.grad_inv_s, s));
+  // forward activations still resident in per-chunk slots?  otherwise recompute chunk by chunk into slot 0
+  const bool cached = c.fwd_cached && c.cached_R == R && c.cached_S == S && c.cached_T == T;
   if (bg) {
     const int rc = c.Mc / T;
-    for (int r0 = 0; r0 < R; r0 += rc) {
+    for (int r0 = 0, ci = 0; r0 < R; r0 += rc, ++ci) {
       const int nr = (R - r0) < rc ? (R - r0) : rc;
       const int M = nr * T;
-      NRW_TRY(nerf_chunk_forward(c, M, io.o + r0 * 3, io.d + r0 * 3, io.sv_z_feed + (long long)r0 * T,
-                                 io.sample_dist + r0, nullptr, io.a_emb + (long long)r0 * c.n_a, T, T, s));
+      c.use_nerf_slot(cached ? ci : 0);
+      if (!cached)
+        NRW_TRY(nerf_chunk_forward(c, M, io.o + r0 * 3, io.d + r0 * 3, io.sv_z_feed + (long long)r0 * T,
+                                   io.sample_dist + r0, nullptr, io.a_emb + (long long)r0 * c.n_a, T, T, s));
       NRW_TRY(nerf_chunk_backward(c, M, c.g_dbga + (long long)r0 * T, c.g_dbgc + (long long)r0 * T * 3,
                                   g.grad_a_emb + (long long)r0 * c.n_a, nr, T, s));
     }
   }
   const int rc = c.Mc / S;
-  for (int r0 = 0; r0 < R; r0 += rc) {
+  for (int r0 = 0, ci = 0; r0 < R; r0 += rc, ++ci) {
     const int nr = (R - r0) < rc ? (R - r0) : rc;
     const int M = nr * S;
-    NRW_TRY(launch_points(io.o + r0 * 3, io.d + r0 * 3, io.z_vals + (long long)r0 * S, io.sample_dist + r0, nr, S, 1, c.PTS, s));
-    NRW_TRY(sdf_chunk_forward(c, M, c.PTS, true, true, s));
-    NRW_TRY(color_chunk_forward(c, M, c.PTS, io.d + r0 * 3, io.a_emb + (long long)r0 * c.n_a, S, s));
+    c.use_sdf_slot(cached ? ci : 0);
+    if (!cached) {
+      NRW_TRY(launch_points(io.o + r0 * 3, io.d + r0 * 3, io.z_vals + (long long)r0 * S, io.sample_dist + r0, nr, S, 1, c.PTS, s));
+      NRW_TRY(sdf_chunk_forward(c, M, c.PTS, true, true, s));
+      NRW_TRY(color_chunk_forward(c, M, c.PTS, io.d + r0 * 3, io.a_emb + (long long)r0 * c.n_a, S, s));
+    }
     NRW_TRY(color_chunk_backward(c, M, c.g_drgb + (long long)r0 * S * 3, c.g_dnrm + (long long)r0 * S * 3, S,
                                  g.grad_a_emb + (long long)r0 * c.n_a, nr, s));
     NRW_TRY(sdf_chunk_backward(c, M, c.PTS, c.g_dsdf + (long long)r0 * S, s));
   }
+  c.fwd_cached = false;
+  c.use_sdf_slot(0);
+  c.use_nerf_slot(0);
   return unpack_grads(c.pm, c.tab, c.params, c.packed, c.gs, g.grad_params, s);
 }
 

@@ -6,8 +6,44 @@
 #include "params.h"
 #include "pointwise.h"
 
+// Forward activations of one chunk.  With enough HBM (180 GB on B200) every chunk of a training batch
+// keeps its own slot, so the backward pass consumes them directly instead of recomputing the forward.
+struct FwdSdfSlot {
+  float* PTS;
+  nrw::Planes U0, U[9], G[8], FEAT;
+  float* A[8];
+  float* Q[8];
+  float *c_sdf, *c_nrm;
+  nrw::Planes IN1, H1, IN2, X[5];
+  float* c_rgb;
+};
+struct FwdNerfSlot {
+  nrw::Planes IN0, NH[9], IN5, FEATN, AP[5];
+  float *c_density, *c_alpha, *c_rgbbg, *c_dists;
+};
+
 struct nrw_ctx {
   int n_planes = 2, backend = 0, n_vocab = 0, n_a = 48;
+  std::vector<FwdSdfSlot> sdf_slots;
+  std::vector<FwdNerfSlot> nerf_slots;
+  int n_slots_sdf = 1, n_slots_nerf = 1;
+  bool fwd_cached = false;          // slots hold the forward of the last render_forward call
+  int cached_R = 0, cached_S = 0, cached_T = 0;
+  void use_sdf_slot(int i) {
+    const FwdSdfSlot& s = sdf_slots[i];
+    PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm;
+    for (int l = 0; l < 9; ++l) U[l] = s.U[l];
+    for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; A[l] = s.A[l]; Q[l] = s.Q[l]; }
+    IN1 = s.IN1; H1 = s.H1; IN2 = s.IN2; c_rgb = s.c_rgb;
+    for (int l = 0; l < 5; ++l) X[l] = s.X[l];
+  }
+  void use_nerf_slot(int i) {
+    const FwdNerfSlot& s = nerf_slots[i];
+    IN0 = s.IN0; IN5 = s.IN5; FEATN = s.FEATN;
+    for (int l = 0; l < 9; ++l) NH[l] = s.NH[l];
+    for (int l = 0; l < 5; ++l) AP[l] = s.AP[l];
+    c_density = s.c_density; c_alpha = s.c_alpha; c_rgbbg = s.c_rgbbg; c_dists = s.c_dists;
+  }
   std::vector<nrw::ParamInfo> tab;
   nrw::PackedModel pm;
   char* packed = nullptr;
@@ -56,9 +92,10 @@ struct nrw_ctx {
 
 namespace nrw {
 
-long long workspace_bytes(const nrw_ctx& c, int chunk_rows, int with_bwd, int max_rays, int max_T);
+long long workspace_bytes(const nrw_ctx& c, int chunk_rows, int with_bwd, int max_rays, int max_T, int n_slots_sdf,
+                          int n_slots_nerf);
 int carve_workspace(nrw_ctx& c, void* base, long long bytes, int chunk_rows, int with_bwd, int max_rays,
-                    int max_T, cudaStream_t s);
+                    int max_T, int n_slots_sdf, int n_slots_nerf, cudaStream_t s);
 
 // SDF value (+ normals, + feature planes) for M rows at positions pts [M,3]; results in c.c_sdf / c.c_nrm / c.FEAT
 int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, bool need_feat, cudaStream_t s);

@@ -29,5 +29,7 @@ inline int gemm(int backend, const GemmDesc& g, cudaStream_t stream) {
 inline int n_products(int n_planes) { return n_planes == 1 ? 1 : (n_planes == 2 ? 3 : 6); }
 
 long long gemm_tc_launch_count();
+// debug: when non-null, every tcgen05 GEMM launch accumulates per-CTA cycle attribution into buf[148*8]
+void gemm_tc_set_profile_buffer(unsigned long long* buf);
 
 }  // namespace nrw

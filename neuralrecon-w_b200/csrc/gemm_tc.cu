@@ -27,7 +27,8 @@ static constexpr int STAGE_BUDGET = 192 * 1024;
 static constexpr int MAX_STAGES = 8;
 static constexpr int N_EPI_WARPS = 8;
 static constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
-static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256;
+static constexpr int STG_BYTES = N_EPI_WARPS * 4096;   // per-warp 32x32 fp32 staging tiles (epilogue)
+static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256 + STG_BYTES;
 
 struct TcParams {
   CUtensorMap tmA[3];
@@ -37,7 +38,14 @@ struct TcParams {
   int k_slices;
   int m_tiles, n_tiles;
   Epi epi;
+  // optional cycle attribution (debug): per CTA 8 counters
+  //  [0] producer: waiting for a free stage   [1] mma: waiting for TMA data   [2] mma: waiting for a free accumulator
+  //  [3] epilogue warp 4: waiting for the accumulator   [4] epilogue warp 4: busy   [5] kernel cycles   [6] tiles
+  unsigned long long* prof;
 };
+#define NRW_PROF_T0(cond) const long long _t0 = (cond) ? clock64() : 0
+#define NRW_PROF_ADD(cond, slot) \
+  if (cond) atomicAdd(&p.prof[blockIdx.x * 16 + (slot)], (unsigned long long)(clock64() - _t0))
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -157,6 +165,237 @@ __device__ __forceinline__ void product_planes(int n_planes, int p, int& pa, int
   pb = tb[q];
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-transposed global I/O of a 32x32 tile through a per-warp shared staging buffer.
+// In the epilogue lane r owns ROW r (TMEM lane) and 32 consecutive columns; a direct 16-byte store
+// would touch 32 different cache lines per instruction.  Staging through shared memory (XOR-swizzled
+// 16-byte slots, conflict-free both ways) lets every global instruction cover whole 128-byte lines.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void wt_store_f32(float* stg, const float (&v)[32], float* dst, long long ld, int rows_valid,
+                                             int cols_valid, int lane, bool atomic) {
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((s ^ (lane & 7)) << 2)) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+  __syncwarp();
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((ld & 3) == 0);
+  const int s = lane & 7, c = s * 4;
+  if (vec_ok && !atomic && rows_valid == 32 && cols_valid == 32) {
+    // full tile (warp-uniform): all shared loads first, then 8 unguarded 16-byte stores of whole lines
+    float4 t[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      t[it] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      *reinterpret_cast<float4*>(dst + (long long)rr * ld + c) = t[it];
+    }
+    __syncwarp();
+    return;
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    const float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2));
+    if (rr < rows_valid && c < cols_valid) {
+      float* g = dst + (long long)rr * ld + c;
+      if (atomic) {
+        atomicAdd(g, t.x);
+        if (c + 1 < cols_valid) atomicAdd(g + 1, t.y);
+        if (c + 2 < cols_valid) atomicAdd(g + 2, t.z);
+        if (c + 3 < cols_valid) atomicAdd(g + 3, t.w);
+      } else if (vec_ok && c + 4 <= cols_valid) {
+        *reinterpret_cast<float4*>(g) = t;
+      } else {
+        g[0] = t.x;
+        if (c + 1 < cols_valid) g[1] = t.y;
+        if (c + 2 < cols_valid) g[2] = t.z;
+        if (c + 3 < cols_valid) g[3] = t.w;
+      }
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void wt_load_f32(float* stg, float (&v)[32], const float* src, long long ld, int rows_valid,
+                                            int cols_valid, int lane) {
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld & 3) == 0);
+  const int s = lane & 7, c = s * 4;
+  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
+    float4 t[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) t[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)(it * 4 + (lane >> 3)) * ld + c));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      *reinterpret_cast<float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2)) = t[it];
+    }
+  } else
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < rows_valid && c < cols_valid) {
+      const float* g = src + (long long)rr * ld + c;
+      if (vec_ok && c + 4 <= cols_valid) {
+        t = __ldg(reinterpret_cast<const float4*>(g));
+      } else {
+        t.x = g[0];
+        if (c + 1 < cols_valid) t.y = g[1];
+        if (c + 2 < cols_valid) t.z = g[2];
+        if (c + 3 < cols_valid) t.w = g[3];
+      }
+    }
+    *reinterpret_cast<float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2)) = t;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2));
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+  __syncwarp();
+}
+// 32 rows x 32 bf16 (64-byte rows): 4 uint4 slots per row, slot' = slot ^ ((row >> 1) & 3)
+__device__ __forceinline__ void wt_store_bf16(float* stg_f, const uint32_t (&pk)[16], bf16* dst, long long ld, int rows_valid,
+                                              int cols_valid, int lane) {
+  uint4* stg = reinterpret_cast<uint4*>(stg_f);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) stg[lane * 4 + (s ^ ((lane >> 1) & 3))] = make_uint4(pk[4 * s], pk[4 * s + 1], pk[4 * s + 2], pk[4 * s + 3]);
+  __syncwarp();
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((ld & 7) == 0);
+  const int s = lane & 3, c = s * 8;
+  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
+    uint4 t[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      t[it] = stg[rr * 4 + (s ^ ((rr >> 1) & 3))];
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(dst + (long long)(it * 8 + (lane >> 2)) * ld + c) = t[it];
+    __syncwarp();
+    return;
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    const uint4 t = stg[rr * 4 + (s ^ ((rr >> 1) & 3))];
+    if (rr < rows_valid && c < cols_valid) {
+      bf16* g = dst + (long long)rr * ld + c;
+      if (vec_ok && c + 8 <= cols_valid) {
+        *reinterpret_cast<uint4*>(g) = t;
+      } else {
+        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c + k < cols_valid) g[k] = __ushort_as_bfloat16((unsigned short)((u[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu));
+      }
+    }
+  }
+  __syncwarp();
+}
+// returns a bit mask: bit j set <=> src[row = lane][col j] > 0
+__device__ __forceinline__ uint32_t wt_load_posmask_bf16(float* stg_f, const bf16* src, long long ld, int rows_valid,
+                                                        int cols_valid, int lane) {
+  uint4* stg = reinterpret_cast<uint4*>(stg_f);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld & 7) == 0);
+  const int s = lane & 3, c = s * 8;
+  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
+    uint4 t[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) t[it] = __ldg(reinterpret_cast<const uint4*>(src + (long long)(it * 8 + (lane >> 2)) * ld + c));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      stg[rr * 4 + (s ^ ((rr >> 1) & 3))] = t[it];
+    }
+  } else
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (rr < rows_valid && c < cols_valid) {
+      const bf16* g = src + (long long)rr * ld + c;
+      if (vec_ok && c + 8 <= cols_valid) {
+        t = __ldg(reinterpret_cast<const uint4*>(g));
+      } else {
+        uint32_t u[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c + k < cols_valid) u[k >> 1] |= (uint32_t)__bfloat16_as_ushort(g[k]) << ((k & 1) * 16);
+        t = make_uint4(u[0], u[1], u[2], u[3]);
+      }
+    }
+    stg[rr * 4 + (s ^ ((rr >> 1) & 3))] = t;
+  }
+  __syncwarp();
+  uint32_t pos = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 t = stg[lane * 4 + (q ^ ((lane >> 1) & 3))];
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = u[k] & 0xFFFFu, hi = u[k] >> 16;
+      if (lo != 0u && lo < 0x8000u) pos |= 1u << (q * 8 + 2 * k);
+      if (hi != 0u && hi < 0x8000u) pos |= 1u << (q * 8 + 2 * k + 1);
+    }
+  }
+  __syncwarp();
+  return pos;
+}
+
+// One 32-row x 32-column chunk of the epilogue for the warp owning TMEM lanes [quarter*32, +32).
+#define NRW_EPI_TICK(slot)                                                     \
+  if (pc) {                                                                    \
+    const long long _now = clock64();                                          \
+    atomicAdd(&pc[slot], (unsigned long long)(_now - _tick));                  \
+    _tick = _now;                                                              \
+  }
+__device__ __forceinline__ void epi_chunk(const Epi& e, float* stg, float (&acc)[32], int m0w, int nc, int M, int N, int lane,
+                                          unsigned long long* pc) {
+  const int rows_valid = min(32, M - m0w);
+  if (rows_valid <= 0) return;
+  long long _tick = pc ? clock64() : 0;
+  const int n_all = min(N - nc, 32);
+  const int n_st = min(e.n_store - nc, n_all);
+  const int m = min(m0w + lane, M - 1);
+  epi_bias<32>(e, m, nc, n_all, acc);
+  if (e.out_pre) wt_store_f32(stg, acc, e.out_pre + (long long)m0w * e.ld_pre + nc, e.ld_pre, rows_valid, n_all, lane, false);
+  NRW_EPI_TICK(9);
+  if (n_st <= 0) return;
+  if (e.atomic) {
+    if (e.scale != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] *= e.scale;
+    }
+    wt_store_f32(stg, acc, e.out_f32 + (long long)m0w * e.ld_f32 + nc, e.ld_f32, rows_valid, n_st, lane, true);
+    return;
+  }
+  float a[32], q[32], ad[32], w[32];
+  uint32_t pos = 0;
+  if (e.aux_sig) wt_load_f32(stg, a, e.aux_sig + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
+  if (e.out2) {
+    if (e.aux_q_bcast) load_f32<32>(e.aux_q + nc, n_st, q);
+    else wt_load_f32(stg, q, e.aux_q + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
+  }
+  if (e.aux_add) wt_load_f32(stg, ad, e.aux_add + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
+  if (e.aux_relu) pos = wt_load_posmask_bf16(stg, e.aux_relu + (long long)m0w * e.ld_relu + nc, e.ld_relu, rows_valid, n_st, lane);
+  NRW_EPI_TICK(10);
+  epi_math<32>(e, acc, a, q, ad, pos, w);
+  NRW_EPI_TICK(11);
+  if (e.out2) wt_store_f32(stg, q, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, rows_valid, n_st, lane, false);
+  if (e.out_f32) wt_store_f32(stg, w, e.out_f32 + (long long)m0w * e.ld_f32 + nc, e.ld_f32, rows_valid, n_st, lane, false);
+  for (int pl = 0; pl < e.n_planes; ++pl) {
+    uint32_t pk[16];
+    split_plane<32>(w, pk);
+    wt_store_bf16(stg, pk, e.out_pl.plane(pl) + (long long)m0w * e.out_pl.ld + nc, e.out_pl.ld, rows_valid, n_st, lane);
+  }
+  NRW_EPI_TICK(12);
+}
+
 template <int BN, int MN_MAJOR>
 __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int A_TILE = BM * BK * 2;
@@ -174,6 +413,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8);
   const uint32_t bar_tfull = smem_u32(bars + 16), bar_tempty = smem_u32(bars + 18);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_kernel0 = clock64();
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < P; ++i) {
@@ -214,7 +454,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int n0 = (t % p.n_tiles) * BN, m0 = (t / p.n_tiles) * BM;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          {
+            NRW_PROF_T0(p.prof != nullptr);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            NRW_PROF_ADD(p.prof != nullptr, 0);
+          }
           mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + P * A_TILE;
@@ -250,12 +494,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int ks = item % p.k_slices;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        {
+          NRW_PROF_T0(p.prof != nullptr);
+          mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+          NRW_PROF_ADD(p.prof != nullptr, 2);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t first = 1;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
+          {
+            NRW_PROF_T0(p.prof != nullptr);
+            mbar_wait(bar_full + 8 * s, ph);
+            NRW_PROF_ADD(p.prof != nullptr, 1);
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + P * A_TILE;
@@ -288,6 +540,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                // column interleave among warps of the same quarter
     constexpr int CH_PER = N_EPI_WARPS / 4;   // warps per quarter
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 1024;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -295,26 +548,40 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       const int t = item / p.k_slices;
       const int n0 = (t % p.n_tiles) * BN, m0 = (t / p.n_tiles) * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
-      mbar_wait(bar_tfull + 8 * acc, acc_ph);
-      tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
-      if (kb1 > kb0) {
-        for (int c = chalf; c < BN / 32; c += CH_PER) {
-          const int nc = n0 + c * 32;
-          if (nc >= p.N) break;               // warp-uniform
-          float v[32];
-          tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
-          if (m < p.M) epi_apply<32>(p.epi, m, nc, v, p.N);
-        }
+      const bool prof = p.prof != nullptr && warp == 4 && lane == 0;
+      {
+        NRW_PROF_T0(prof);
+        mbar_wait(bar_tfull + 8 * acc, acc_ph);
+        NRW_PROF_ADD(prof, 3);
       }
-      tc_fence_before();
-      __syncwarp();
+      tc_fence_after();
+      {
+        NRW_PROF_T0(prof);
+        if (kb1 > kb0) {
+          for (int c = chalf; c < BN / 32; c += CH_PER) {
+            const int nc = n0 + c * 32;
+            if (nc >= p.N) break;               // warp-uniform
+            float v[32];
+            {
+              NRW_PROF_T0(prof);
+              tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+              NRW_PROF_ADD(prof, 8);
+            }
+            epi_chunk(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, prof ? p.prof + blockIdx.x * 16 : nullptr);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        NRW_PROF_ADD(prof, 4);
+        if (prof) atomicAdd(&p.prof[blockIdx.x * 16 + 6], 1ull);
+      }
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.prof && threadIdx.x == 0) atomicAdd(&p.prof[blockIdx.x * 16 + 5], (unsigned long long)(clock64() - t_kernel0));
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -388,6 +655,8 @@ static int make_map(CUtensorMap* out, const bf16* ptr, long long inner, long lon
   return NRW_OK;
 }
 
+static unsigned long long* g_prof_ptr = nullptr;
+void gemm_tc_set_profile_buffer(unsigned long long* p) { g_prof_ptr = p; }
 static long long g_tc_launches = 0;
 long long gemm_tc_launch_count() { return g_tc_launches; }
 
@@ -417,14 +686,17 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     NRW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   int BN;
+  static const int bn_pref = getenv("NRW_TC_BN") ? atoi(getenv("NRW_TC_BN")) : 0;   // tuning override
   if (g.N <= 64) BN = 64;
-  else if (g.N <= 128 || g.n_planes >= 2) BN = 128;
-  else BN = 256;
+  else if (g.N <= 128 || g.n_planes >= 3) BN = 128;
+  else if (g.n_planes == 2) BN = (bn_pref == 256) ? 256 : 128;
+  else BN = (bn_pref == 128) ? 128 : 256;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = g.M; p.N = g.N; p.K = g.K; p.n_planes = g.n_planes; p.k_slices = g.k_slices;
   p.m_tiles = cdiv(g.M, BM); p.n_tiles = cdiv(g.N, BN);
   p.epi = g.epi;
+  p.prof = g_prof_ptr;
   for (int pl = 0; pl < g.n_planes; ++pl) {
     if (!g.mn_major) {
       NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);

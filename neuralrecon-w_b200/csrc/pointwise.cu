@@ -31,32 +31,6 @@ int launch_points(const float* o, const float* d, const float* z, const float* s
   return NRW_OK;
 }
 
-// ---- SDF positional encoding (L=6, 39 wide; models/neuconw.py:7-55) -----------------------------
-// U0[m, 0:64] = [x, sin(2^k x), cos(2^k x) ..., 0 pad];  U4[m, 473:512] = PE / sqrt(2)
-__global__ void sdf_embed_kernel(const float* __restrict__ pts, int M, int n_planes, Planes U0, Planes U4) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float pe[39];
-  const float x0 = pts[m * 3], x1 = pts[m * 3 + 1], x2 = pts[m * 3 + 2];
-  pe[0] = x0; pe[1] = x1; pe[2] = x2;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float f = (float)(1 << k);
-    float s, c;
-    sincosf(x0 * f, &s, &c); pe[3 + 6 * k] = s; pe[6 + 6 * k] = c;
-    sincosf(x1 * f, &s, &c); pe[4 + 6 * k] = s; pe[7 + 6 * k] = c;
-    sincosf(x2 * f, &s, &c); pe[5 + 6 * k] = s; pe[8 + 6 * k] = c;
-  }
-  for (int j = 0; j < 64; ++j) planes_store(U0, n_planes, (long long)m * U0.ld + j, j < 39 ? pe[j] : 0.0f);
-  if (U4.p)
-    for (int j = 0; j < 39; ++j) planes_store(U4, n_planes, (long long)m * U4.ld + 473 + j, pe[j] * INV_SQRT2);
-}
-int launch_sdf_embed(const float* pts, int M, int n_planes, Planes U0, Planes U4, cudaStream_t s) {
-  sdf_embed_kernel<<<cdiv(M, 128), 128, 0, s>>>(pts, M, n_planes, U0, U4);
-  NRW_LAUNCH_OK();
-  return NRW_OK;
-}
-
 // ---- SDF head: sdf = softplus(a7) . w0 + b0 ; optional gbar7 = softplus'(a7) * w0 ------------------
 __global__ void __launch_bounds__(256) sdf_head_kernel(const float* __restrict__ A7, int M,
                                                        const float* __restrict__ w0,
@@ -134,130 +108,6 @@ __global__ void sdf_normal_bwd_kernel(const float* __restrict__ pts, const float
 int launch_sdf_normal_bwd(const float* pts, const float* dn, int M, int n_planes, Planes DQ0, Planes DQ4,
                           cudaStream_t s) {
   sdf_normal_bwd_kernel<<<cdiv(M, 128), 128, 0, s>>>(pts, dn, M, n_planes, DQ0, DQ4);
-  NRW_LAUNCH_OK();
-  return NRW_OK;
-}
-
-// ---- view-direction PE (L=4, 27 wide) + appearance code + geometry inputs for the colour net --------
-// IN1[m, 512:640] = [viewPE(d) 27 | a n_a | 0];  IN2[m, 128:192] = [pts 3 | normal 3 | 0]
-__global__ void color_embed_kernel(const float* __restrict__ dirs, const float* __restrict__ a, int n_a,
-                                   int rows_per_src, const float* __restrict__ pts,
-                                   const float* __restrict__ nrm, int M, int n_planes, Planes IN1, Planes IN2) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int r = m / rows_per_src;
-  float pe[27];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float x = dirs[r * 3 + c];
-    pe[c] = x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float sn, cs;
-      sincosf(x * (float)(1 << k), &sn, &cs);
-      pe[3 + 6 * k + c] = sn;
-      pe[6 + 6 * k + c] = cs;
-    }
-  }
-  const long long b1 = (long long)m * IN1.ld + 512;
-  for (int j = 0; j < 128; ++j) {
-    float v = 0.0f;
-    if (j < 27) v = pe[j];
-    else if (j < 27 + n_a) v = a[(long long)r * n_a + (j - 27)];
-    planes_store(IN1, n_planes, b1 + j, v);
-  }
-  const long long b2 = (long long)m * IN2.ld + 128;
-  for (int j = 0; j < 64; ++j) {
-    float v = 0.0f;
-    if (j < 3) v = pts[m * 3 + j];
-    else if (j < 6) v = nrm[m * 3 + (j - 3)];
-    planes_store(IN2, n_planes, b2 + j, v);
-  }
-}
-int launch_color_embed(const float* dirs, const float* a, int n_a, int rows_per_src, const float* pts,
-                       const float* nrm, int M, int n_planes, Planes IN1, Planes IN2, cudaStream_t s) {
-  color_embed_kernel<<<cdiv(M, 128), 128, 0, s>>>(dirs, a, n_a, rows_per_src, pts, nrm, M, n_planes, IN1, IN2);
-  NRW_LAUNCH_OK();
-  return NRW_OK;
-}
-
-// ---- background NeRF inputs (renderer.py:157-203; models/nerf.py:156-160) -----------------------------
-// mode 0: from rays: z_feed [R,T] -> dists, mid, p = o + d*mid, r = clip(|p|,1,1e10), pts4 = [p/r, 1/r]
-// mode 1: explicit pts4 [M,4] (dirs/a per point when rows_per_src == 1)
-// IN0[m,0:128] = [PE10(pts4) 84 | 0]; IN5[m,256:384] = same; FEATN[m,256:384] = [viewPE 27 | a | 0]
-__global__ void nerf_embed_kernel(const float* __restrict__ o, const float* __restrict__ d,
-                                  const float* __restrict__ z, const float* __restrict__ sample_dist,
-                                  const float* __restrict__ pts4_in, const float* __restrict__ a, int n_a,
-                                  int T, int rows_per_src, int M, int n_planes, Planes IN0, Planes IN5,
-                                  Planes FEATN, float* __restrict__ dists_out) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int r = m / rows_per_src;
-  float p4[4];
-  if (pts4_in) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) p4[c] = pts4_in[(long long)m * 4 + c];
-  } else {
-    const int i = m % T;
-    const float t0 = z[m];
-    const float dist = (i + 1 < T) ? __fsub_rn(z[m + 1], t0) : sample_dist[r];
-    const float mid = __fadd_rn(t0, __fmul_rn(dist, 0.5f));
-    float p[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(o[r * 3 + c], __fmul_rn(d[r * 3 + c], mid));
-    float nr = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-    nr = fminf(fmaxf(nr, 1.0f), 1e10f);
-    p4[0] = p[0] / nr; p4[1] = p[1] / nr; p4[2] = p[2] / nr; p4[3] = 1.0f / nr;
-    if (dists_out) dists_out[m] = dist;
-  }
-  const long long b0 = (long long)m * IN0.ld, b5 = (long long)m * IN5.ld + 256;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    planes_store(IN0, n_planes, b0 + c, p4[c]);
-    planes_store(IN5, n_planes, b5 + c, p4[c]);
-  }
-  for (int k = 0; k < 10; ++k) {
-    const float f = (float)(1 << k);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float sn, cs;
-      sincosf(p4[c] * f, &sn, &cs);
-      planes_store(IN0, n_planes, b0 + 4 + 8 * k + c, sn);
-      planes_store(IN0, n_planes, b0 + 8 + 8 * k + c, cs);
-      planes_store(IN5, n_planes, b5 + 4 + 8 * k + c, sn);
-      planes_store(IN5, n_planes, b5 + 8 + 8 * k + c, cs);
-    }
-  }
-  for (int j = 84; j < 128; ++j) {
-    planes_store(IN0, n_planes, b0 + j, 0.0f);
-    planes_store(IN5, n_planes, b5 + j, 0.0f);
-  }
-  float pe[27];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float x = d[r * 3 + c];
-    pe[c] = x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float sn, cs;
-      sincosf(x * (float)(1 << k), &sn, &cs);
-      pe[3 + 6 * k + c] = sn;
-      pe[6 + 6 * k + c] = cs;
-    }
-  }
-  const long long bf = (long long)m * FEATN.ld + 256;
-  for (int j = 0; j < 128; ++j) {
-    float v = 0.0f;
-    if (j < 27) v = pe[j];
-    else if (j < 27 + n_a) v = a[(long long)r * n_a + (j - 27)];
-    planes_store(FEATN, n_planes, bf + j, v);
-  }
-}
-int launch_nerf_embed(const float* o, const float* d, const float* z, const float* sample_dist,
-                      const float* pts4_in, const float* a, int n_a, int T, int rows_per_src, int M,
-                      int n_planes, Planes IN0, Planes IN5, Planes FEATN, float* dists_out, cudaStream_t s) {
-  nerf_embed_kernel<<<cdiv(M, 128), 128, 0, s>>>(o, d, z, sample_dist, pts4_in, a, n_a, T, rows_per_src, M,
-                                                 n_planes, IN0, IN5, FEATN, dists_out);
   NRW_LAUNCH_OK();
   return NRW_OK;
 }
@@ -376,34 +226,6 @@ int launch_head_bwd(int nout, Planes X, int n_planes, int K, int M, const float*
     head_bwd_kernel<1><<<grid, 256, smem, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
   else
     head_bwd_kernel<3><<<grid, 256, smem, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
-  NRW_LAUNCH_OK();
-  return NRW_OK;
-}
-
-// ---- column sums: out[n] += sum_m X[m,n]  (bias gradients) ----------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(Planes X, int n_planes, const float* __restrict__ Xf, int ld,
-                                                     int M, int N, const float* __restrict__ rowscale,
-                                                     float* __restrict__ out, float* __restrict__ out_rs) {
-  // block handles 256 rows x all columns; thread t owns columns t, t+256, ...
-  const int row0 = blockIdx.x * 256, row1 = min(M, row0 + 256);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float acc = 0.0f;
-    for (int m = row0; m < row1; ++m) {
-      float v = Xf ? Xf[(long long)m * ld + n] : planes_load(X, n_planes, (long long)m * X.ld + n);
-      if (rowscale) v *= rowscale[m];
-      acc += v;
-    }
-    atomicAdd(&out[n], acc);
-  }
-  if (out_rs && threadIdx.x == 0) {
-    float acc = 0.0f;
-    for (int m = row0; m < row1; ++m) acc += rowscale[m];
-    atomicAdd(out_rs, acc);
-  }
-}
-int launch_colsum(Planes X, int n_planes, const float* Xf, int ld, int M, int N, const float* rowscale,
-                  float* out, float* out_rowscale_sum, cudaStream_t s) {
-  colsum_kernel<<<cdiv(M, 256), 256, 0, s>>>(X, n_planes, Xf, ld, M, N, rowscale, out, out_rowscale_sum);
   NRW_LAUNCH_OK();
   return NRW_OK;
 }

@@ -71,8 +71,8 @@ def lib():
     L.nrw_packed_bytes.restype = ll
     L.nrw_packed_bytes.argtypes = [vp]
     L.nrw_workspace_bytes.restype = ll
-    L.nrw_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
-    L.nrw_ctx_bind.argtypes = [vp, vp, ll, vp, ll, i32, i32, i32, i32, vp]
+    L.nrw_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+    L.nrw_ctx_bind.argtypes = [vp, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, vp]
     L.nrw_pack_weights.argtypes = [vp, vp, vp]
     L.nrw_sdf_query.argtypes = [vp, vp, ll, vp, vp]
     L.nrw_neuconw_forward.argtypes = [vp, vp, vp, vp, ll, vp, vp, vp, vp]
@@ -90,6 +90,7 @@ def lib():
     L.nrw_gemm_test_scratch_bytes.argtypes = [i32, i32, i32]
     L.nrw_gemm_test.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]
     L.nrw_launch_count.restype = ll
+    L.nrw_debug_gemm_profile.argtypes = [vp]
     _lib = L
     return L
 
@@ -99,7 +100,7 @@ EXPORTS = ["nrw_last_error", "nrw_version", "nrw_param_count", "nrw_param_table"
            "nrw_pack_weights", "nrw_sdf_query", "nrw_neuconw_forward", "nrw_nerf_forward", "nrw_sample",
            "nrw_samples_per_ray", "nrw_upsample_round", "nrw_render_forward", "nrw_render_backward",
            "nrw_composite_forward", "nrw_composite_backward", "nrw_octree_near_far", "nrw_octree_hits",
-           "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count"]
+           "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile"]
 
 
 def check(status, what=""):

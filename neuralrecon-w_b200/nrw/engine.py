@@ -90,7 +90,10 @@ class Engine:
         return named
 
     # ---- context / workspace ----------------------------------------------------------------
-    def ensure(self, device, max_rays, max_T, with_backward):
+    def ensure(self, device, max_rays, max_T, with_backward, S=None):
+        """(Re)bind the workspace.  With backward enabled, as many chunk slots as the memory budget
+        (NRW_SLOT_BUDGET_GB, default 60 % of free HBM) allows keep their forward activations resident so
+        the backward pass does not recompute the forward (the 180 GB of a B200 hold a full 8192x128 batch)."""
         max_rays = max(int(max_rays), 1)
         max_T = max(int(max_T), 2)
         chunk = max(self.chunk_rows, ((max_T + 127) // 128) * 128)
@@ -105,15 +108,28 @@ class Engine:
             if self.packed is None or self.packed.device != device:
                 nb = self.L.nrw_packed_bytes(self.ctx)
                 self.packed = torch.empty(nb + 1024, dtype=torch.uint8, device=device)
-            wb = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T)
             self.workspace = None
+            torch.cuda.empty_cache()
+            ns_sdf = ns_nerf = 1
+            if with_backward and os.environ.get("NRW_RECOMPUTE", "0") != "1":
+                S_eff = int(S) if S else max_T
+                want_sdf = -(-max_rays // max(chunk // S_eff, 1))
+                want_nerf = -(-max_rays // max(chunk // max_T, 1))
+                free, _total = torch.cuda.mem_get_info(device)
+                budget = float(os.environ.get("NRW_SLOT_BUDGET_GB", 0)) * 2 ** 30 or 0.6 * free
+                need = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T, want_sdf, want_nerf)
+                if need <= budget:
+                    ns_sdf, ns_nerf = want_sdf, want_nerf
+            wb = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T, ns_sdf, ns_nerf)
             self.workspace = torch.empty(wb + 2048, dtype=torch.uint8, device=device)
             pk = (self.packed.data_ptr() + 1023) // 1024 * 1024
             ws = (self.workspace.data_ptr() + 1023) // 1024 * 1024
             check(self.L.nrw_ctx_bind(self.ctx, C.c_void_p(pk), self.packed.numel() - (pk - self.packed.data_ptr()),
                                       C.c_void_p(ws), self.workspace.numel() - (ws - self.workspace.data_ptr()),
-                                      chunk, with_backward, max_rays, max_T, stream_ptr()), "nrw_ctx_bind")
+                                      chunk, with_backward, max_rays, max_T, ns_sdf, ns_nerf, stream_ptr()),
+                  "nrw_ctx_bind")
         self.bound = (max_rays, max_T, with_backward, chunk)
+        self.slots = (ns_sdf, ns_nerf)
 
     def pack(self, device):
         named = self.flatten(device)
@@ -184,7 +200,7 @@ class Engine:
         dev = o.device
         need_grad = torch.is_grad_enabled()
         T = rcfg.S + rcfg.n_outside
-        self.ensure(dev, rcfg.R, T, int(need_grad))
+        self.ensure(dev, rcfg.R, T, int(need_grad), S=rcfg.S)
         named = self.pack(dev)
         params = [p for _, p in named]
         outs = _RenderFn.apply(self, rcfg, o, d, z_vals, z_out, sample_dist, a_emb, inv_s, *params)
