@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("NRW_PRECISION", "bf16x3"))
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0)
-    ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 32768)))
+    ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 262144)))
     ap.add_argument("--cpu_rays", type=int, default=32)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_torch_gpu_ref", action="store_true")

@@ -156,7 +156,7 @@ static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t
   GemmDesc g;
   g.A = dY; g.B = X; g.n_planes = c.n_planes;
   g.M = L.Np; g.N = L.Kp; g.K = M; g.mn_major = 1;
-  const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.n_planes >= 2) ? 128 : 256);
+  const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.n_planes >= 3) ? 128 : 256);
   const int tiles = cdiv(g.M, 128) * cdiv(g.N, bn);
   int ks = 296 / tiles;
   const int max_ks = M / 512 > 0 ? M / 512 : 1;
@@ -283,17 +283,18 @@ int color_chunk_backward(nrw_ctx& c, int M, const float* d_rgb, const float* d_n
   const Heads& H = c.pm.heads;
   NRW_TRY(launch_head_bwd(3, c.X[4], P, 256, M, c.f_area + H.cl4_w, d_rgb, c.c_rgb, nullptr, 1, c.dX[0], nullptr,
                           c.gs + H.d_cl4_w, c.gs + H.d_cl4_b, s));
+  // bias gradients = column sums of each layer's pre-activation gradient; fused into the epilogue of the GEMM
+  // that PRODUCES that gradient (Epi::colsum), only the head-produced one needs its own pass
   int cur = 0;
+  NRW_TRY(bias_grad(c, c.dX[0], M, L_CL0 + 3, s));
   for (int l = 3; l >= 1; --l) {
     NRW_TRY(mm_dw(c, c.dX[cur], c.X[l], M, L_CL0 + l, s));
-    NRW_TRY(bias_grad(c, c.dX[cur], M, L_CL0 + l, s));
-    Epi e; e.aux_relu = c.X[l].p; e.ld_relu = 256; e.out_pl = c.dX[1 - cur];
+    Epi e; e.aux_relu = c.X[l].p; e.ld_relu = 256; e.out_pl = c.dX[1 - cur]; e.colsum = c.db(L_CL0 + l - 1);
     NRW_TRY(mm(c, c.dX[cur], c.WT(L_CL0 + l), M, 256, 256, e, s));
     cur = 1 - cur;
   }
   NRW_TRY(mm_dw(c, c.dX[cur], c.IN2, M, L_CL0, s));
-  NRW_TRY(bias_grad(c, c.dX[cur], M, L_CL0, s));
-  { Epi e; e.aux_relu = c.IN2.p; e.ld_relu = 192; e.out_pl = c.dH2;
+  { Epi e; e.aux_relu = c.IN2.p; e.ld_relu = 192; e.out_pl = c.dH2; e.colsum = c.db(L_CS1);
     NRW_TRY(mm(c, c.dX[cur], c.WT(L_CL0), M, 128, 256, e, s)); }
   { Epi e; e.out_f32 = c.tail; e.ld_f32 = 64;
     NRW_TRY(mm(c, c.dX[cur], rows(c.WT(L_CL0), 128), M, 64, 256, e, s)); }
@@ -301,20 +302,17 @@ int color_chunk_backward(nrw_ctx& c, int M, const float* d_rgb, const float* d_n
   NRW_LAUNCH_OK();
   // static_linear_1: H1 -> IN2[:, :128]
   NRW_TRY(mm_dw(c, c.dH2, c.H1, M, L_CS1, s));
-  NRW_TRY(bias_grad(c, c.dH2, M, L_CS1, s));
-  { Epi e; e.aux_relu = c.H1.p; e.ld_relu = 128; e.out_pl = c.dH1;
+  { Epi e; e.aux_relu = c.H1.p; e.ld_relu = 128; e.out_pl = c.dH1; e.colsum = c.db(L_CS0);
     NRW_TRY(mm(c, c.dH2, c.WT(L_CS1), M, 128, 128, e, s)); }
   // static_linear_0: IN1 [xf | viewPE | a] -> H1
   NRW_TRY(mm_dw(c, c.dH1, c.IN1, M, L_CS0, s));
-  NRW_TRY(bias_grad(c, c.dH1, M, L_CS0, s));
-  { Epi e; e.out_pl = c.dXF; NRW_TRY(mm(c, c.dH1, c.WT(L_CS0), M, 512, 128, e, s)); }
+  { Epi e; e.out_pl = c.dXF; e.colsum = c.db(L_CX); NRW_TRY(mm(c, c.dH1, c.WT(L_CS0), M, 512, 128, e, s)); }
   { Epi e; e.out_f32 = c.tail; e.ld_f32 = 128;
     NRW_TRY(mm(c, c.dH1, rows(c.WT(L_CS0), 512), M, 128, 128, e, s)); }
   if (d_a_rays) NRW_TRY(launch_segsum(c.tail, 128, 27, c.n_a, R_chunk, rows_per_src, d_a_rays, 1, s));
   // xyz_encoding_final: FEAT -> IN1[:, :512]
   NRW_TRY(mm_dw(c, c.dXF, c.FEAT, M, L_CX, s));
-  NRW_TRY(bias_grad(c, c.dXF, M, L_CX, s));
-  { Epi e; e.out_pl = c.DFEAT; NRW_TRY(mm(c, c.dXF, c.WT(L_CX), M, 512, 512, e, s)); }
+  { Epi e; e.out_pl = c.DFEAT; e.colsum = c.db(L_SDF8F); NRW_TRY(mm(c, c.dXF, c.WT(L_CX), M, 512, 512, e, s)); }
   return NRW_OK;
 }
 
@@ -345,28 +343,27 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
   }
   NRW_TRY(launch_colsum(Planes{nullptr, 0, 0}, P, c.DQ8f, 512, M, 512, nullptr, c.gs + H.d_sdf_w0, nullptr, s));
   // reverse sweep
-  NRW_TRY(mm_dw(c, c.DFEAT, c.U[8], M, L_SDF8F, s));
-  NRW_TRY(bias_grad(c, c.DFEAT, M, L_SDF8F, s));
+  NRW_TRY(mm_dw(c, c.DFEAT, c.U[8], M, L_SDF8F, s));   // (db of lin8[1:] was accumulated by the colour backward)
   NRW_TRY(launch_colsum(c.U[8], P, nullptr, 0, M, 512, d_sdf, c.gs + H.d_sdf_w0, c.gs + H.d_sdf_b0, s));
   {
     Epi e;
     e.rowvec = d_sdf; e.colvec = w0;
     e.aux_sig = c.A[7]; e.aux_add = c.DA2[7]; e.ld_aux = 512;
     e.out_pl = c.DA[1];
+    e.colsum = c.db(L_SDF0 + 7);
     NRW_TRY(mm(c, c.DFEAT, c.WT(L_SDF8F), M, 512, 512, e, s));
   }
   for (int l = 7; l >= 1; --l) {
     Planes cur = c.DA[l & 1];
     NRW_TRY(mm_dw(c, cur, c.U[l], M, L_SDF0 + l, s));
-    NRW_TRY(bias_grad(c, cur, M, L_SDF0 + l, s));
     Epi e;
     e.aux_sig = c.A[l - 1]; e.aux_add = c.DA2[l - 1]; e.ld_aux = 512;
     e.out_pl = c.DA[(l - 1) & 1];
+    e.colsum = c.db(L_SDF0 + l - 1);
     if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }
     NRW_TRY(mm(c, cur, c.WT(L_SDF0 + l), M, 512, 512, e, s));
   }
   NRW_TRY(mm_dw(c, c.DA[0], c.U0, M, L_SDF0, s));
-  NRW_TRY(bias_grad(c, c.DA[0], M, L_SDF0, s));
   return NRW_OK;
 }
 
@@ -377,16 +374,15 @@ int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bg
   NRW_TRY(launch_head_bwd(3, c.AP[4], P, 128, M, c.f_area + H.nr_w, d_bgc, nullptr, nullptr, 0, c.dNA[0], nullptr,
                           c.gs + H.d_nr_w, c.gs + H.d_nr_b, s));
   int cur = 0;
+  NRW_TRY(bias_grad(c, c.dNA[0], M, L_NS0 + 3, s));
   for (int l = 3; l >= 1; --l) {
     NRW_TRY(mm_dw(c, c.dNA[cur], c.AP[l], M, L_NS0 + l, s));
-    NRW_TRY(bias_grad(c, c.dNA[cur], M, L_NS0 + l, s));
-    Epi e; e.aux_relu = c.AP[l].p; e.ld_relu = 128; e.out_pl = c.dNA[1 - cur];
+    Epi e; e.aux_relu = c.AP[l].p; e.ld_relu = 128; e.out_pl = c.dNA[1 - cur]; e.colsum = c.db(L_NS0 + l - 1);
     NRW_TRY(mm(c, c.dNA[cur], c.WT(L_NS0 + l), M, 128, 128, e, s));
     cur = 1 - cur;
   }
   NRW_TRY(mm_dw(c, c.dNA[cur], c.FEATN, M, L_NS0, s));
-  NRW_TRY(bias_grad(c, c.dNA[cur], M, L_NS0, s));
-  { Epi e; e.out_pl = c.dNF; NRW_TRY(mm(c, c.dNA[cur], c.WT(L_NS0), M, 256, 128, e, s)); }
+  { Epi e; e.out_pl = c.dNF; e.colsum = c.db(L_NF); NRW_TRY(mm(c, c.dNA[cur], c.WT(L_NS0), M, 256, 128, e, s)); }
   { Epi e; e.out_f32 = c.tail; e.ld_f32 = 128;
     NRW_TRY(mm(c, c.dNA[cur], rows(c.WT(L_NS0), 256), M, 128, 128, e, s)); }
   if (d_a_rays) NRW_TRY(launch_segsum(c.tail, 128, 27, c.n_a, R_chunk, T, d_a_rays, 1, s));
@@ -395,21 +391,18 @@ int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bg
                           Planes{nullptr, 0, 0}, c.c_ddens, c.gs + H.d_na_w, c.gs + H.d_na_b, s));
   // feature_linear: NH[8] -> FEATN[:, :256]
   NRW_TRY(mm_dw(c, c.dNF, c.NH[8], M, L_NF, s));
-  NRW_TRY(bias_grad(c, c.dNF, M, L_NF, s));
   { Epi e; e.rowvec = c.c_ddens; e.colvec = c.f_area + H.na_w; e.aux_relu = c.NH[8].p; e.ld_relu = 256;
-    e.out_pl = c.dNH[0];
+    e.out_pl = c.dNH[0]; e.colsum = c.db(L_N0 + 7);
     NRW_TRY(mm(c, c.dNF, c.WT(L_NF), M, 256, 256, e, s)); }
   cur = 0;
   for (int l = 7; l >= 1; --l) {
     Planes Xin = (l == 5) ? c.IN5 : c.NH[l];
     NRW_TRY(mm_dw(c, c.dNH[cur], Xin, M, L_N0 + l, s));
-    NRW_TRY(bias_grad(c, c.dNH[cur], M, L_N0 + l, s));
-    Epi e; e.aux_relu = Xin.p; e.ld_relu = Xin.ld; e.out_pl = c.dNH[1 - cur];
+    Epi e; e.aux_relu = Xin.p; e.ld_relu = Xin.ld; e.out_pl = c.dNH[1 - cur]; e.colsum = c.db(L_N0 + l - 1);
     NRW_TRY(mm(c, c.dNH[cur], c.WT(L_N0 + l), M, 256, 256, e, s));  // first 256 WT rows = the h part for l==5
     cur = 1 - cur;
   }
   NRW_TRY(mm_dw(c, c.dNH[cur], c.IN0, M, L_N0, s));
-  NRW_TRY(bias_grad(c, c.dNH[cur], M, L_N0, s));
   return NRW_OK;
 }
 

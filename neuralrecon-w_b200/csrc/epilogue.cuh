@@ -42,6 +42,7 @@ struct Epi {
   Planes out_pl = {nullptr, 0, 0};
   int n_planes = 0;
   int n_store = 1 << 30;  // column bound for out_f32 / out_pl / out2
+  float* colsum = nullptr;  // += sum over rows of the main output w (bias gradient of the producing layer)
 };
 
 // ---- vector helpers: NC consecutive floats / bf16 of one row -------------------------------------
@@ -201,6 +202,11 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n0, float (&a
       if (j < n_st && __bfloat162float(e.aux_relu[(long long)m * e.ld_relu + n0 + j]) > 0.0f) pos |= 1u << j;
   }
   epi_math<NC>(e, acc, a, q, ad, pos, w);
+  if (e.colsum) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < n_st) atomicAdd(e.colsum + n0 + j, w[j]);
+  }
   if (e.out2) store_f32<NC>(e.out2 + (long long)m * e.ld_out2 + n0, n_st, q);
   if (e.out_f32) store_f32<NC>(e.out_f32 + (long long)m * e.ld_f32 + n0, n_st, w);
   if (e.n_planes > 0) store_planes<NC>(e.out_pl, e.n_planes, (long long)m * e.out_pl.ld + n0, n_st, w);

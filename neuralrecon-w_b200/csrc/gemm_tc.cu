@@ -386,6 +386,17 @@ __device__ __forceinline__ void epi_chunk(const Epi& e, float* stg, float (&acc)
   NRW_EPI_TICK(10);
   epi_math<32>(e, acc, a, q, ad, pos, w);
   NRW_EPI_TICK(11);
+  if (e.colsum) {
+    // column sums of the 32x32 tile through the staging buffer: lane j owns column j (conflict-free reads)
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      *reinterpret_cast<float4*>(stg + lane * 32 + ((s ^ (lane & 7)) << 2)) = make_float4(w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
+    __syncwarp();
+    float cs = 0.0f;
+    for (int r = 0; r < rows_valid; ++r) cs += stg[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+    if (lane < n_st) atomicAdd(e.colsum + nc + lane, cs);
+    __syncwarp();
+  }
   if (e.out2) wt_store_f32(stg, q, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, rows_valid, n_st, lane, false);
   if (e.out_f32) wt_store_f32(stg, w, e.out_f32 + (long long)m0w * e.ld_f32 + nc, e.ld_f32, rows_valid, n_st, lane, false);
   for (int pl = 0; pl < e.n_planes; ++pl) {
@@ -588,6 +599,223 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   }
 }
 
+// =======================================================================================
+// CTA-pair variant: tcgen05.mma.cta_group::2, one 256 x 256 tile per pair of SMs.
+//   Each CTA of the pair stages its own 128 rows of A and HALF of B (128 of the 256 weight rows); the
+//   leader CTA's single MMA thread issues M=256 instructions that read both CTAs' shared memory and
+//   write both CTAs' TMEM.  Per MMA-flop this halves the shared-memory operand reads and the L2->SMEM
+//   traffic of the 1-CTA kernel (which is shared-memory-bandwidth bound at N<=256).
+//   Barriers: full[s] lives on the leader and collects the TMA bytes of BOTH CTAs (.cta_group::2 loads
+//   with the peer bit of the mbarrier address cleared); empty[s] / tmem_full[] are signalled in both
+//   CTAs by multicast tcgen05.commit; tmem_empty[] on the leader collects both epilogues.
+// =======================================================================================
+static constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address
+static constexpr int BN2 = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+
+template <int MN_MAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  constexpr int A_TILE = BM * BK * 2;              // this CTA's 128 rows of A
+  constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
+  constexpr int TMEM_COLS = 2 * BN2;               // two 256-column accumulators
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int P = p.n_planes;
+  const int stage_bytes = P * (A_TILE + B_TILE);
+  int stages = STAGE_BUDGET / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8);
+  const uint32_t bar_tfull = smem_u32(bars + 16), bar_tempty = smem_u32(bars + 18);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P; ++i) {
+      tma_prefetch_desc(&p.tmA[i]);
+      tma_prefetch_desc(&p.tmB[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 2 * N_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.k_slices - 1) / p.k_slices;
+  const int n_items = p.m_tiles * p.n_tiles * p.k_slices;   // m_tiles counts 256-row tiles
+  const int n_prod = (P == 1) ? 1 : (P == 2 ? 3 : 6);
+  const int unit = blockIdx.x >> 1, n_units = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = unit; item < n_items; item += n_units) {
+        const int ks = item % p.k_slices;
+        const int t = item / p.k_slices;
+        const int n0 = (t % p.n_tiles) * BN2 + (int)rank * (BN2 / 2);
+        const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
+          const uint32_t bfl = (bar_full + 8 * s) & PEER_MASK;
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + P * A_TILE;
+          for (int pl = 0; pl < P; ++pl) {
+            if (MN_MAJOR == 0) {
+              tma_load_2d_2sm(sa + pl * A_TILE, &p.tmA[pl], bfl, kb * BK, m0);
+              tma_load_2d_2sm(sb + pl * B_TILE, &p.tmB[pl], bfl, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int sl = 0; sl < 2; ++sl) {
+                tma_load_2d_2sm(sa + pl * A_TILE + sl * (64 * BK * 2), &p.tmA[pl], bfl, m0 + 64 * sl, kb * BK);
+                tma_load_2d_2sm(sb + pl * B_TILE + sl * (64 * BK * 2), &p.tmB[pl], bfl, n0 + 64 * sl, kb * BK);
+              }
+            }
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MN_MAJOR << 15) | ((uint32_t)MN_MAJOR << 16) |
+                                 ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      constexpr uint32_t LBO = MN_MAJOR ? (64 * BK * 2) : 16;
+      constexpr uint32_t SBO = 1024;
+      constexpr uint32_t KSTEP = MN_MAJOR ? (16 * 128) : 32;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (int item = unit; item < n_items; item += n_units) {
+        const int ks = item % p.k_slices;
+        const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        uint32_t first = 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + P * A_TILE;
+          for (int pr = 0; pr < n_prod; ++pr) {
+            int pa, pb;
+            product_planes(P, pr, pa, pb);
+            const uint64_t da = make_sdesc(sa + pa * A_TILE, LBO, SBO);
+            const uint64_t db = make_sdesc(sb + pb * B_TILE, LBO, SBO);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_2sm(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          umma_commit_2sm(bar_empty + 8 * s);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int chalf = ew >> 2;
+    constexpr int CH_PER = N_EPI_WARPS / 4;
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 1024;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = unit; item < n_items; item += n_units) {
+      const int ks = item % p.k_slices;
+      const int t = item / p.k_slices;
+      const int n0 = (t % p.n_tiles) * BN2;
+      const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
+      const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      if (kb1 > kb0) {
+        for (int c = chalf; c < BN2 / 32; c += CH_PER) {
+          const int nc = n0 + c * 32;
+          if (nc >= p.N) break;
+          float v[32];
+          tmem_ld32(tmem_base + acc * BN2 + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+          epi_chunk(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, nullptr);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still signal our barriers / read our shared memory until here
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side: tensor maps (driver entry point fetched at run time: no link-time libcuda)
 // ---------------------------------------------------------------------------------------
@@ -689,7 +917,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   static const int bn_pref = getenv("NRW_TC_BN") ? atoi(getenv("NRW_TC_BN")) : 0;   // tuning override
   if (g.N <= 64) BN = 64;
   else if (g.N <= 128 || g.n_planes >= 3) BN = 128;
-  else if (g.n_planes == 2) BN = (bn_pref == 256) ? 256 : 128;
+  else if (g.n_planes == 2) BN = (bn_pref == 128) ? 128 : 256;   // 2 TMA stages of 96 KB, N=256 MMAs
   else BN = (bn_pref == 128) ? 128 : 256;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -697,6 +925,35 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.m_tiles = cdiv(g.M, BM); p.n_tiles = cdiv(g.N, BN);
   p.epi = g.epi;
   p.prof = g_prof_ptr;
+  // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) for the wide layers
+  static const int use_2cta = getenv("NRW_TC_2CTA") ? atoi(getenv("NRW_TC_2CTA")) : 1;
+  if (use_2cta && g.N >= 256 && g.M >= 256) {
+    p.m_tiles = cdiv(g.M, 2 * BM); p.n_tiles = cdiv(g.N, BN2);
+    for (int pl = 0; pl < g.n_planes; ++pl) {
+      if (!g.mn_major) {
+        NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);
+        NRW_TRY(make_map(&p.tmA[pl], g.A.plane(pl), g.K, g.M, g.A.ld, BK, BM));
+        NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.K, g.N, g.B.ld, BK, BN2 / 2));
+      } else {
+        NRW_TRY(make_map(&p.tmA[pl], g.A.plane(pl), g.M, g.K, g.A.ld, 64, BK));
+        NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.N, g.K, g.B.ld, 64, BK));
+      }
+    }
+    static bool attr2[2] = {false, false};
+    if (!attr2[g.mn_major ? 1 : 0]) {
+      if (g.mn_major) NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      else NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr2[g.mn_major ? 1 : 0] = true;
+    }
+    const int items = p.m_tiles * p.n_tiles * p.k_slices;
+    int pairs = n_sm / 2;
+    if (items < pairs) pairs = items;
+    if (g.mn_major) gemm_tc2_kernel<1><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
+    else gemm_tc2_kernel<0><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
+    NRW_LAUNCH_OK();
+    ++g_tc_launches;
+    return NRW_OK;
+  }
   for (int pl = 0; pl < g.n_planes; ++pl) {
     if (!g.mn_major) {
       NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);

@@ -37,7 +37,7 @@ class Engine:
             raise NrwError(f"unknown precision {self.precision!r}; choose from {sorted(PRECISIONS)}")
         self.n_planes = PRECISIONS[self.precision]
         self.backend = default_backend() if backend is None else backend
-        self.chunk_rows = int(chunk_rows or os.environ.get("NRW_CHUNK_ROWS", 32768))
+        self.chunk_rows = int(chunk_rows or os.environ.get("NRW_CHUNK_ROWS", 262144))
         self.table, self.total = _lib.param_table(self.n_vocab, self.n_a)
         self.index = {name: (shape, off, numel) for name, shape, off, numel in self.table}
         self.ctx = C.c_void_p()
@@ -94,16 +94,16 @@ class Engine:
         """(Re)bind the workspace.  With backward enabled, as many chunk slots as the memory budget
         (NRW_SLOT_BUDGET_GB, default 60 % of free HBM) allows keep their forward activations resident so
         the backward pass does not recompute the forward (the 180 GB of a B200 hold a full 8192x128 batch)."""
-        max_rays = max(int(max_rays), 1)
-        max_T = max(int(max_T), 2)
-        chunk = max(self.chunk_rows, ((max_T + 127) // 128) * 128)
         b = self.bound
-        if (self.workspace is not None and self.workspace.device == device and b[0] >= max_rays and b[1] >= max_T
-                and b[2] >= int(with_backward) and b[3] == chunk):
+        if (self.workspace is not None and self.workspace.device == device and b[0] >= int(max_rays) and b[1] >= int(max_T)
+                and b[2] >= int(with_backward)):
             return
-        max_rays = max(max_rays, b[0])
-        max_T = max(max_T, b[1])
+        max_rays = max(int(max_rays), 1, b[0])
+        max_T = max(int(max_T), 2, b[1])
         with_backward = max(int(with_backward), b[2])
+        # chunk: as large as configured, but never (much) larger than the whole problem
+        need_rows = ((max_rays * max_T + 127) // 128) * 128
+        chunk = max(min(self.chunk_rows, max(need_rows, 4096)), ((max_T + 127) // 128) * 128)
         with torch.cuda.device(device):
             if self.packed is None or self.packed.device != device:
                 nb = self.L.nrw_packed_bytes(self.ctx)
@@ -140,8 +140,8 @@ class Engine:
     def sdf(self, pts):
         """SDF values for pts [n,3] -> [n] (NeuconWRenderer.sdf, rendering/renderer.py:947-949)."""
         pts = pts.detach().reshape(-1, 3).contiguous().float()
-        dev = pts.device
-        self.ensure(dev, 1, 2, 0)
+        n, dev = pts.shape[0], pts.device
+        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
         self.pack(dev)
         out = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
         check(self.L.nrw_sdf_query(self.ctx, ptr(pts), pts.shape[0], ptr(out), stream_ptr()), "nrw_sdf_query")
@@ -150,7 +150,7 @@ class Engine:
     def neuconw_forward(self, pts, dirs, a, want_rgb=True):
         pts = pts.detach().reshape(-1, 3).contiguous().float()
         n, dev = pts.shape[0], pts.device
-        self.ensure(dev, 1, 2, 0)
+        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
         self.pack(dev)
         sdf = torch.empty(n, dtype=torch.float32, device=dev)
         nrm = torch.empty(n, 3, dtype=torch.float32, device=dev)
@@ -164,7 +164,7 @@ class Engine:
     def nerf_forward(self, pts4, dirs, a):
         pts4 = pts4.detach().reshape(-1, 4).contiguous().float()
         n, dev = pts4.shape[0], pts4.device
-        self.ensure(dev, 1, 2, 0)
+        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
         self.pack(dev)
         dens = torch.empty(n, 1, dtype=torch.float32, device=dev)
         rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)

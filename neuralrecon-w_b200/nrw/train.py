@@ -75,11 +75,16 @@ class TrainSystem:
         """training_step + backward + DDP-mean all-reduce + clip(0.99) + Adam (neuconw_system.py:337-360,
         train.py:61).  Returns the detached loss tensor (device)."""
         rays, rgbs, ts, label = batch["rays"], batch["rgbs"], batch["ts"], batch["label"]
+        ev = getattr(self, "stage_events", None)       # optional [(name, cuda event)] list for stage timing
+        mark = (lambda n: ev.append((n, _rec()))) if ev is not None else (lambda n: None)
+        mark("start")
         self.renderer.nerf_far_override = False
         self.optimizer.zero_grad(set_to_none=True)
         results = self.forward(rays, ts, label)
+        mark("forward")
         loss = sum(self.loss(results, rgbs).values())
         loss.backward()
+        mark("backward")
         eng = self.renderer.engine
         flat = eng.last_flat_grad
         for k, p in eng.named_params():        # make every .grad a view of the flat gradient buffer
@@ -94,5 +99,12 @@ class TrainSystem:
                 eg.div_(self.world_size)
         torch.nn.utils.clip_grad_norm_(self.params, 0.99)
         self.optimizer.step()
+        mark("optimizer")
         self.global_step += 1
         return loss.detach()
+
+
+def _rec():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
