@@ -140,52 +140,20 @@ def torch_gpu_reference(workload, n_rays, steps, device):
     return n_rays / (ms * 1e-3), ms
 
 
-def gemm_microbench(device, n_planes):
-    """Dominant kernel alone: one 512x512 SDF layer over 65536 samples (tcgen05 GEMM + softplus epilogue)."""
-    import ctypes as C
-    from nrw import _lib
-
-    L = _lib.lib()
-    M, N, K = 65536, 512, 512
-    A = torch.randn(M, K, device=device)
-    B = torch.randn(N, K, device=device) / 22.0
-    bias = torch.zeros(N, device=device)
-    D = torch.empty(M, N, device=device)
-    scratch = torch.empty(L.nrw_gemm_test_scratch_bytes(M, N, K) + 1024, dtype=torch.uint8, device=device)
-    sp = (scratch.data_ptr() + 1023) // 1024 * 1024
-    # flush-sized filler so operands do not sit in L2 between iterations
-    filler = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-    ts = []
-    for it in range(8):
-        filler.zero_()
-        torch.cuda.synchronize()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        # includes the plane-split pre-pass; time the GEMM by differencing with a split-only call is overkill:
-        # the split kernels are ~10% of this call, reported as-is (conservative)
-        t0.record()
-        _lib.check(L.nrw_gemm_test(0, n_planes, 0, 1, M, N, K, _lib.ptr(A), _lib.ptr(B), _lib.ptr(bias), 1, _lib.ptr(D),
-                                   C.c_void_p(sp), _lib.stream_ptr()), "gemm_test")
-        t1.record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            ts.append(t0.elapsed_time(t1))
-    ms = sorted(ts)[len(ts) // 2]
-    return 2.0 * M * N * K / (ms * 1e-3) / 1e12, ms
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nrw", choices=["nrw", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NRW_PRECISION", "bf16x3"))
+    ap.add_argument("--precision", default=os.environ.get("NRW_PRECISION", "bf16x3"), choices=["bf16x3", "mixed", "bf16", "bf16x6"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 262144)))
     ap.add_argument("--cpu_rays", type=int, default=32)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_torch_gpu_ref", action="store_true")
+    ap.add_argument("--no_other_modes", action="store_true")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.rays:
@@ -280,29 +248,67 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     flops_step = flop_per_ray(w) * R
     peak_tf, peak_hbm, peak_src = peaks()
-    achieved_tf = flops_step / (ms * 1e-3) / 1e12
+    DTYPES = {"bf16": "bf16", "bf16x3": "bf16 (3-product split, fp32 accumulate)", "bf16x6": "bf16 (6-product split, fp32 accumulate)",
+              "mixed": "bf16 (3-product split forward, plain bf16 backward, fp32 accumulate)"}
+    # ---- roofline of the dominant kernel: CUDA events around EVERY tcgen05 GEMM launch of two more steps ----
+    import ctypes as C
+    L.nrw_gemm_timing(1, None)
+    run(2, False)
+    torch.cuda.synchronize()
+    out4 = (C.c_double * 4)()
+    L.nrw_gemm_timing(0, out4)
+    k_ms, k_flop, k_mma, k_n = out4[0] / 2, out4[1] / 2, out4[2] / 2, out4[3] / 2
+    achieved_tf = k_flop / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     line = {"metric": "training rays/sec", "value": R * world / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16 (3-product split, fp32 accumulate)",
-                                                            "bf16x6": "bf16 (6-product split, fp32 accumulate)"}[args.precision],
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": config, "precision_mode": args.precision, "loss": float(loss),
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
-                         "kernel": "gemm_tc_kernel (all dense layers of the step; algorithmic FLOP = 4.66 GFLOP/ray x rays)",
-                         "algorithmic_tflop_per_step": flops_step / 1e12}}
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 GEMM of every dense layer)",
+                         "launches_per_step": k_n, "kernel_ms_per_step": k_ms, "share_of_step": k_ms / ms,
+                         "algorithmic_tflop_per_step_in_kernel": k_flop / 1e12,
+                         "mma_tflops_incl_split_products": k_mma / (k_ms * 1e-3) / 1e12,
+                         "mma_frac_of_peak": k_mma / (k_ms * 1e-3) / 1e12 / peak_tf,
+                         "step_level": {"algorithmic_tflop_per_step": flops_step / 1e12,
+                                        "achieved": flops_step / (ms * 1e-3) / 1e12,
+                                        "frac": flops_step / (ms * 1e-3) / 1e12 / peak_tf}}}
     if world == 1:
-        try:
-            tf, gms = gemm_microbench(device, {"bf16": 1, "bf16x3": 2, "bf16x6": 3}[args.precision])
-            line["roofline"]["gemm_kernel"] = {"shape": "M=65536 N=512 K=512 (one SDF layer + softplus epilogue)",
-                                               "achieved": tf, "unit": "TFLOP/s (algorithmic 2MNK)", "ms": gms,
-                                               "frac": tf / peak_tf}
-        except Exception as e:  # noqa
-            line["roofline"]["gemm_kernel"] = {"error": str(e)[:200]}
+        if not args.no_other_modes:
+            others = {}
+            for mode in ("mixed", "bf16"):
+                if mode == args.precision:
+                    continue
+                try:
+                    del sysm
+                    torch.cuda.empty_cache()
+                    sysm = TrainSystem(device, n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=k,
+                                       n_outside=w["n_outside"], precision=mode, chunk_rows=args.chunk_rows,
+                                       batch_size=w["rays"], world_size=1, seed=66)
+                    for _ in range(3):
+                        sysm.training_step(dev_batch)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(args.steps):
+                        sysm.training_step(dev_batch)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    m = e0.elapsed_time(e1) / args.steps
+                    others[mode] = {"value": R / (m * 1e-3), "unit": "rays/s", "ms_per_step": m, "dtype": DTYPES[mode]}
+                except Exception as e:  # noqa
+                    others[mode] = {"error": str(e)[:200]}
+            line["other_precision_modes"] = others
         if not args.no_torch_gpu_ref:
             try:
+                sysm = None
+                torch.cuda.empty_cache()
                 rps, rms = torch_gpu_reference(args.workload, 1024, 3, device)
                 line["reference_torch_gpu"] = {"value": rps, "unit": "rays/s", "ms_per_step": rms,
                                                "sample": f"1024 rays x {S} samples, stock torch fp32 ops of the reference path on this GPU"}

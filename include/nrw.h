@@ -65,6 +65,9 @@ NRW_API long long nrw_param_total(int n_vocab, int n_a);
  * products ~ fp32).  chunk_rows: samples per MLP chunk (multiple of 128). */
 NRW_API int nrw_ctx_create(nrw_ctx** out, int n_planes, int gemm_backend, int n_vocab, int n_a);
 NRW_API int nrw_ctx_destroy(nrw_ctx* ctx);
+/* mixed precision: the backward GEMMs use only the first n operand planes (0 = same as forward).  n = 1 with
+ * n_planes = 2 keeps every rendered output at split-bf16 accuracy and computes gradients in plain bf16. */
+NRW_API int nrw_ctx_set_backward_planes(nrw_ctx* ctx, int n);
 NRW_API long long nrw_packed_bytes(const nrw_ctx* ctx);
 /* n_slots_sdf / n_slots_nerf: how many chunks keep their forward activations resident for the backward pass
  * (>= number of chunks of a batch: no forward recompute in backward; 1: recompute, minimum memory). */
@@ -205,7 +208,11 @@ NRW_API int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices,
                           const float* A, const float* B, const float* bias, int act, float* D,
                           void* scratch, void* stream);
 NRW_API long long nrw_launch_count(void);
-/* debug: per-CTA cycle attribution of the tcgen05 GEMM (u64 [SMs,8], zeroed by the caller; NULL = off) */
+/* measurement: while enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its stream; a call with
+ * out4 != NULL synchronises those events and returns {sum of kernel ms, algorithmic FLOP (2MNK), MMA FLOP
+ * (x plane products), launches} since the last read (bench.py roofline). */
+NRW_API int nrw_gemm_timing(int enable, double* out4_host);
+/* debug: per-CTA cycle attribution of the tcgen05 GEMM (u64 [SMs,16], zeroed by the caller; NULL = off) */
 NRW_API int nrw_debug_gemm_profile(void* device_buf_u64);
 
 #ifdef __cplusplus

@@ -59,6 +59,13 @@ int nrw_ctx_create(nrw_ctx** out, int n_planes, int gemm_backend, int n_vocab, i
   return NRW_OK;
   NRW_GUARD_END
 }
+int nrw_ctx_set_backward_planes(nrw_ctx* ctx, int n) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(ctx && n >= 0 && n <= ctx->n_planes, NRW_ERR_ARG, "set_backward_planes: n=%d out of range", n);
+  ctx->bwd_planes = n;
+  return NRW_OK;
+  NRW_GUARD_END
+}
 int nrw_ctx_destroy(nrw_ctx* ctx) {
   delete ctx;
   return NRW_OK;
@@ -251,6 +258,17 @@ int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices, int M, 
   NRW_GUARD_END
 }
 long long nrw_launch_count(void) { return g_kernel_launches; }
+int nrw_gemm_timing(int enable, double* out4 /* host: ms, algorithmic FLOP, MMA FLOP, launches; may be NULL */) {
+  NRW_GUARD_BEGIN
+  if (out4) {
+    long long n = 0;
+    NRW_TRY(gemm_tc_timing_read(&out4[0], &out4[1], &out4[2], &n));
+    out4[3] = (double)n;
+  }
+  gemm_tc_timing_enable(enable != 0);
+  return NRW_OK;
+  NRW_GUARD_END
+}
 int nrw_debug_gemm_profile(void* device_buf_u64_148x8) {
   gemm_tc_set_profile_buffer(reinterpret_cast<unsigned long long*>(device_buf_u64_148x8));
   return NRW_OK;

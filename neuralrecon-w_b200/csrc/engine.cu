@@ -145,8 +145,8 @@ int carve_workspace(nrw_ctx& c, void* base, long long bytes, int chunk_rows, int
 // ---------------------------------------------------------------------------------------------
 static int mm(nrw_ctx& c, Planes A, Planes B, int M, int N, int K, Epi e, cudaStream_t s) {
   GemmDesc g;
-  g.A = A; g.B = B; g.n_planes = c.n_planes; g.M = M; g.N = N; g.K = K; g.mn_major = 0; g.k_slices = 1;
-  if (e.out_pl.p) e.n_planes = c.n_planes;
+  g.A = A; g.B = B; g.n_planes = c.cur_planes; g.M = M; g.N = N; g.K = K; g.mn_major = 0; g.k_slices = 1;
+  if (e.out_pl.p) e.n_planes = c.cur_planes;
   g.epi = e;
   return gemm(c.backend, g, s);
 }
@@ -154,9 +154,9 @@ static int mm(nrw_ctx& c, Planes A, Planes B, int M, int N, int K, Epi e, cudaSt
 static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t s) {
   const PackedLayer& L = c.pm.layers[layer];
   GemmDesc g;
-  g.A = dY; g.B = X; g.n_planes = c.n_planes;
+  g.A = dY; g.B = X; g.n_planes = c.cur_planes;
   g.M = L.Np; g.N = L.Kp; g.K = M; g.mn_major = 1;
-  const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.n_planes >= 3) ? 128 : 256);
+  const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.cur_planes >= 3) ? 128 : 256);
   const int tiles = cdiv(g.M, 128) * cdiv(g.N, bn);
   int ks = 296 / tiles;
   const int max_ks = M / 512 > 0 ? M / 512 : 1;
@@ -173,7 +173,7 @@ static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t
   return gemm(c.backend, g, s);
 }
 static int bias_grad(nrw_ctx& c, Planes dY, int M, int layer, cudaStream_t s) {
-  return launch_colsum(dY, c.n_planes, nullptr, 0, M, c.pm.layers[layer].Np, nullptr, c.db(layer), nullptr, s);
+  return launch_colsum(dY, c.cur_planes, nullptr, 0, M, c.pm.layers[layer].Np, nullptr, c.db(layer), nullptr, s);
 }
 static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld, P.pstride, P.ld}; }
 
@@ -181,6 +181,7 @@ static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld,
 // forward chunks
 // ---------------------------------------------------------------------------------------------
 int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, bool need_feat, cudaStream_t s) {
+  c.cur_planes = c.n_planes;
   const int P = c.n_planes;
   NRW_TRY(launch_sdf_embed(pts, M, P, c.U0, c.U[4], s));
   for (int l = 0; l < 8; ++l) {
@@ -220,6 +221,7 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
 
 int color_chunk_forward(nrw_ctx& c, int M, const float* pts, const float* dirs, const float* a, int rows_per_src,
                         cudaStream_t s) {
+  c.cur_planes = c.n_planes;
   const int P = c.n_planes;
   NRW_TRY(launch_color_embed(dirs, a, c.n_a, rows_per_src, pts, c.c_nrm, M, P, c.IN1, c.IN2, s));
   { Epi e; e.bias = c.bias(L_CX); e.out_pl = c.IN1; NRW_TRY(mm(c, c.FEAT, c.W(L_CX), M, 512, 512, e, s)); }
@@ -237,6 +239,7 @@ int color_chunk_forward(nrw_ctx& c, int M, const float* pts, const float* dirs, 
 
 int nerf_chunk_forward(nrw_ctx& c, int M, const float* o, const float* d, const float* z, const float* sdist,
                        const float* pts4, const float* a, int T, int rows_per_src, cudaStream_t s) {
+  c.cur_planes = c.n_planes;
   const int P = c.n_planes;
   NRW_TRY(launch_nerf_embed(o, d, z, sdist, pts4, a, c.n_a, T, rows_per_src, M, P, c.IN0, c.IN5, c.FEATN,
                             pts4 ? nullptr : c.c_dists, s));
@@ -279,7 +282,8 @@ __global__ void add_normal_grad_kernel(float* __restrict__ dn, const float* __re
 // = d_nrm_comp + colour-net contribution) and accumulates per-ray appearance-code gradients.
 int color_chunk_backward(nrw_ctx& c, int M, const float* d_rgb, const float* d_nrm_comp, int rows_per_src,
                          float* d_a_rays, int R_chunk, cudaStream_t s) {
-  const int P = c.n_planes;
+  c.cur_planes = c.bwd_planes > 0 ? c.bwd_planes : c.n_planes;   // 'mixed' mode: backward GEMMs in plain bf16
+  const int P = c.cur_planes;
   const Heads& H = c.pm.heads;
   NRW_TRY(launch_head_bwd(3, c.X[4], P, 256, M, c.f_area + H.cl4_w, d_rgb, c.c_rgb, nullptr, 1, c.dX[0], nullptr,
                           c.gs + H.d_cl4_w, c.gs + H.d_cl4_b, s));
@@ -324,7 +328,8 @@ static Planes dq_buf(nrw_ctx& c, int l) {
 
 // d_sdf [M], c.c_dn [M,3], c.DFEAT -> parameter gradients of the SDF net (second-order backward)
 int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, cudaStream_t s) {
-  const int P = c.n_planes;
+  c.cur_planes = c.bwd_planes > 0 ? c.bwd_planes : c.n_planes;   // 'mixed' mode: backward GEMMs in plain bf16
+  const int P = c.cur_planes;
   const Heads& H = c.pm.heads;
   const float* w0 = c.f_area + H.sdf_w0;
   NRW_TRY(launch_sdf_normal_bwd(pts, c.c_dn, M, P, c.DQ0, c.DQ4, s));
@@ -369,7 +374,8 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
 
 int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bgc, float* d_a_rays, int R_chunk,
                         int T, cudaStream_t s) {
-  const int P = c.n_planes;
+  c.cur_planes = c.bwd_planes > 0 ? c.bwd_planes : c.n_planes;   // 'mixed' mode: backward GEMMs in plain bf16
+  const int P = c.cur_planes;
   const Heads& H = c.pm.heads;
   NRW_TRY(launch_head_bwd(3, c.AP[4], P, 128, M, c.f_area + H.nr_w, d_bgc, nullptr, nullptr, 0, c.dNA[0], nullptr,
                           c.gs + H.d_nr_w, c.gs + H.d_nr_b, s));

@@ -24,6 +24,8 @@ struct FwdNerfSlot {
 
 struct nrw_ctx {
   int n_planes = 2, backend = 0, n_vocab = 0, n_a = 48;
+  int bwd_planes = 0;   // 0: same as n_planes; 1: 'mixed' precision (backward GEMMs use the hi plane only)
+  int cur_planes = 2;   // planes used by the GEMM helpers of the pass in flight
   std::vector<FwdSdfSlot> sdf_slots;
   std::vector<FwdNerfSlot> nerf_slots;
   int n_slots_sdf = 1, n_slots_nerf = 1;

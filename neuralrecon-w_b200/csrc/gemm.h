@@ -31,5 +31,8 @@ inline int n_products(int n_planes) { return n_planes == 1 ? 1 : (n_planes == 2 
 long long gemm_tc_launch_count();
 // debug: when non-null, every tcgen05 GEMM launch accumulates per-CTA cycle attribution into buf[148*8]
 void gemm_tc_set_profile_buffer(unsigned long long* buf);
+// measurement: CUDA events around every tcgen05 GEMM launch (on the launching stream)
+void gemm_tc_timing_enable(bool on);
+int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches);
 
 }  // namespace nrw

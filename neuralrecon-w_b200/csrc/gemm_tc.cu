@@ -14,8 +14,11 @@
 // * mn_major=1 consumes both operands "transposed" straight from their natural row-major
 //   [rows=K][cols=M|N] layout (MN-major UMMA descriptors) - used for weight gradients
 //   dW = dY^T X with split-K over the sample dimension and fp32 atomics in the epilogue.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "gemm.h"
 
@@ -903,7 +906,49 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   return NRW_OK;
 }
 
+static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream);
+
+// ---- live kernel timing (bench.py roofline): CUDA events around every launch on the launching stream ----
+struct TimedLaunch { cudaEvent_t e0, e1; double flops; double mma_flops; };
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+static bool g_timing_on = false;
+void gemm_tc_timing_enable(bool on) { g_timing_on = on; }
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// sums (and clears) the recorded launches: total kernel ms, algorithmic FLOP (2MNK), MMA FLOP (x products), count
+int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches) {
+  double t = 0, f = 0, mf = 0;
+  for (auto& L : g_timed) {
+    NRW_CUDA_OK(cudaEventSynchronize(L.e1));
+    float dt = 0;
+    NRW_CUDA_OK(cudaEventElapsedTime(&dt, L.e0, L.e1));
+    t += dt; f += L.flops; mf += L.mma_flops;
+    g_event_pool.push_back(L.e0); g_event_pool.push_back(L.e1);
+  }
+  *ms = t; *flops = f; *mma_flops = mf; *launches = (long long)g_timed.size();
+  g_timed.clear();
+  return NRW_OK;
+}
+
 int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
+  if (!g_timing_on) return gemm_tc_impl(g, stream);
+  TimedLaunch L;
+  L.e0 = get_event(); L.e1 = get_event();
+  L.flops = 2.0 * g.M * g.N * g.K;
+  L.mma_flops = L.flops * n_products(g.n_planes);
+  NRW_CUDA_OK(cudaEventRecord(L.e0, stream));
+  const int rc = gemm_tc_impl(g, stream);
+  NRW_CUDA_OK(cudaEventRecord(L.e1, stream));
+  g_timed.push_back(L);
+  return rc;
+}
+
+static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   NRW_CHECK(g.M > 0 && g.N > 0 && g.K > 0, NRW_ERR_ARG, "gemm_tc: empty problem %d %d %d", g.M, g.N, g.K);
   NRW_CHECK(g.n_planes >= 1 && g.n_planes <= 3, NRW_ERR_ARG, "gemm_tc: n_planes=%d", g.n_planes);
   NRW_CHECK(g.k_slices == 1 || g.epi.atomic, NRW_ERR_ARG, "gemm_tc: split-K needs an atomic epilogue");

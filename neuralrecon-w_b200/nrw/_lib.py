@@ -68,6 +68,7 @@ def lib():
     L.nrw_param_total.argtypes = [i32, i32]
     L.nrw_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
     L.nrw_ctx_destroy.argtypes = [vp]
+    L.nrw_ctx_set_backward_planes.argtypes = [vp, i32]
     L.nrw_packed_bytes.restype = ll
     L.nrw_packed_bytes.argtypes = [vp]
     L.nrw_workspace_bytes.restype = ll
@@ -91,6 +92,7 @@ def lib():
     L.nrw_gemm_test.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]
     L.nrw_launch_count.restype = ll
     L.nrw_debug_gemm_profile.argtypes = [vp]
+    L.nrw_gemm_timing.argtypes = [i32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -100,7 +102,8 @@ EXPORTS = ["nrw_last_error", "nrw_version", "nrw_param_count", "nrw_param_table"
            "nrw_pack_weights", "nrw_sdf_query", "nrw_neuconw_forward", "nrw_nerf_forward", "nrw_sample",
            "nrw_samples_per_ray", "nrw_upsample_round", "nrw_render_forward", "nrw_render_backward",
            "nrw_composite_forward", "nrw_composite_backward", "nrw_octree_near_far", "nrw_octree_hits",
-           "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile"]
+           "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile",
+           "nrw_gemm_timing", "nrw_ctx_set_backward_planes"]
 
 
 def check(status, what=""):

@@ -10,7 +10,8 @@ import torch
 from . import _lib
 from ._lib import NrwError, RenderCfg, RenderGrads, RenderIO, SamplerCfg, check, ptr, stream_ptr
 
-PRECISIONS = {"bf16": 1, "bf16x3": 2, "bf16x6": 3}
+# name -> (forward planes, backward planes; 0 = same).  "mixed": bf16x3 forward, plain bf16 backward GEMMs.
+PRECISIONS = {"bf16": (1, 0), "bf16x3": (2, 0), "bf16x6": (3, 0), "mixed": (2, 1)}
 
 
 def default_precision():
@@ -35,7 +36,7 @@ class Engine:
         self.precision = precision or default_precision()
         if self.precision not in PRECISIONS:
             raise NrwError(f"unknown precision {self.precision!r}; choose from {sorted(PRECISIONS)}")
-        self.n_planes = PRECISIONS[self.precision]
+        self.n_planes, self.bwd_planes = PRECISIONS[self.precision]
         self.backend = default_backend() if backend is None else backend
         self.chunk_rows = int(chunk_rows or os.environ.get("NRW_CHUNK_ROWS", 262144))
         self.table, self.total = _lib.param_table(self.n_vocab, self.n_a)
@@ -43,6 +44,8 @@ class Engine:
         self.ctx = C.c_void_p()
         check(self.L.nrw_ctx_create(C.byref(self.ctx), self.n_planes, self.backend, self.n_vocab, self.n_a),
               "nrw_ctx_create")
+        if self.bwd_planes:
+            check(self.L.nrw_ctx_set_backward_planes(self.ctx, self.bwd_planes), "nrw_ctx_set_backward_planes")
         self.flat = None
         self.packed = None
         self.workspace = None

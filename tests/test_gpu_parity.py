@@ -249,3 +249,9 @@ def test_full_size_properties():
     before = sysm.renderer.engine.flat.clone()
     loss = sysm.training_step(b)
     assert torch.isfinite(loss) and not torch.equal(before, sysm.renderer.engine.flat)
+
+
+def test_train_step_mixed_precision(P):
+    """'mixed': split-bf16 (3 products) forward -> outputs hold 1e-4; backward GEMMs in plain bf16."""
+    cfg = synth.PathConfig(n_samples=16, n_importance=8, up_sample_steps=2, n_outside=4)
+    _check_step(P, cfg, 48, "mixed", 0, RTOL, 3e-2)
