@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 262144)))
-    ap.add_argument("--cpu_rays", type=int, default=32)
+    ap.add_argument("--cpu_rays", type=int, default=128)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_torch_gpu_ref", action="store_true")
     ap.add_argument("--no_other_modes", action="store_true")
@@ -171,7 +171,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
+        threads = min(os.cpu_count() or 1, 64)   # beyond ~64 threads MKL on these layer sizes slows down
         rps, dt = cpu_reference(args.workload, args.cpu_rays, max(1, min(args.steps, 3)), 1 if args.warmup else 0, threads)
         line = {"impl": "reference", "metric": "training rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
                 "steps": max(1, min(args.steps, 3)), "warmup": 1 if args.warmup else 0, "ms_per_step": dt * 1e3,
@@ -287,7 +287,9 @@ def main():
                 if mode == args.precision:
                     continue
                 try:
-                    del sysm
+                    sysm = None                      # free the previous system's 90 GB of activation slots first
+                    import gc
+                    gc.collect()
                     torch.cuda.empty_cache()
                     sysm = TrainSystem(device, n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=k,
                                        n_outside=w["n_outside"], precision=mode, chunk_rows=args.chunk_rows,
@@ -308,6 +310,8 @@ def main():
         if not args.no_torch_gpu_ref:
             try:
                 sysm = None
+                import gc
+                gc.collect()
                 torch.cuda.empty_cache()
                 rps, rms = torch_gpu_reference(args.workload, 1024, 3, device)
                 line["reference_torch_gpu"] = {"value": rps, "unit": "rays/s", "ms_per_step": rms,
@@ -315,7 +319,7 @@ def main():
             except Exception as e:  # noqa
                 line["reference_torch_gpu"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 64)   # beyond ~64 threads MKL on these layer sizes slows down
             rps, dt = cpu_reference(args.workload, args.cpu_rays, 2, 1, threads)
             line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_rays} rays x {S} samples per step, 2 timed steps (render+loss+backward, torch CPU fp32)"}
