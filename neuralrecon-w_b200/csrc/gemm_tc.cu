@@ -19,8 +19,11 @@
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+#include <algorithm>
+#include <stdio.h>
 
 #include "gemm.h"
+#include "epilogue_tc.cuh"
 
 namespace nrw {
 
@@ -28,10 +31,12 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 static constexpr int STAGE_BUDGET = 192 * 1024;
 static constexpr int MAX_STAGES = 8;
-static constexpr int N_EPI_WARPS = 8;
+static constexpr int N_EPI_WARPS = 16;          // 4 per TMEM lane quarter, 16-column chunks (epilogue_tc.cuh)
 static constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
-static constexpr int STG_BYTES = N_EPI_WARPS * 4096;   // per-warp 32x32 fp32 staging tiles (epilogue)
-static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256 + STG_BYTES;
+static constexpr int STG_BYTES = N_EPI_WARPS * 2048;   // per-warp 32x16 fp32 staging tiles (epilogue)
+static constexpr int CS_BYTES = 1024;                  // per-CTA column-sum accumulator (256 columns of one n-tile)
+static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256 + STG_BYTES + CS_BYTES;
+static_assert(SMEM_BYTES <= 232448, "dynamic shared memory limit of sm_100");
 
 struct TcParams {
   CUtensorMap tmA[3];
@@ -45,6 +50,7 @@ struct TcParams {
   //  [0] producer: waiting for a free stage   [1] mma: waiting for TMA data   [2] mma: waiting for a free accumulator
   //  [3] epilogue warp 4: waiting for the accumulator   [4] epilogue warp 4: busy   [5] kernel cycles   [6] tiles
   unsigned long long* prof;
+  int dbg;   // tuning experiments (NRW_TC_DBG): bit0 = epilogue only drains TMEM, bit1 = one MMA per k-block
 };
 #define NRW_PROF_T0(cond) const long long _t0 = (cond) ? clock64() : 0
 #define NRW_PROF_ADD(cond, slot) \
@@ -122,22 +128,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // UMMA shared-memory descriptor, 128B swizzle, version 1 (sm_100).
@@ -166,248 +168,6 @@ __device__ __forceinline__ void product_planes(int n_planes, int p, int& pa, int
   const int tb[6] = {0, 0, 1, 1, 0, 2};
   pa = ta[q];
   pb = tb[q];
-}
-
-// ---------------------------------------------------------------------------------------
-// Warp-transposed global I/O of a 32x32 tile through a per-warp shared staging buffer.
-// In the epilogue lane r owns ROW r (TMEM lane) and 32 consecutive columns; a direct 16-byte store
-// would touch 32 different cache lines per instruction.  Staging through shared memory (XOR-swizzled
-// 16-byte slots, conflict-free both ways) lets every global instruction cover whole 128-byte lines.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void wt_store_f32(float* stg, const float (&v)[32], float* dst, long long ld, int rows_valid,
-                                             int cols_valid, int lane, bool atomic) {
-#pragma unroll
-  for (int s = 0; s < 8; ++s)
-    *reinterpret_cast<float4*>(stg + lane * 32 + ((s ^ (lane & 7)) << 2)) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
-  __syncwarp();
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((ld & 3) == 0);
-  const int s = lane & 7, c = s * 4;
-  if (vec_ok && !atomic && rows_valid == 32 && cols_valid == 32) {
-    // full tile (warp-uniform): all shared loads first, then 8 unguarded 16-byte stores of whole lines
-    float4 t[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3);
-      t[it] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2));
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3);
-      *reinterpret_cast<float4*>(dst + (long long)rr * ld + c) = t[it];
-    }
-    __syncwarp();
-    return;
-  }
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    const float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2));
-    if (rr < rows_valid && c < cols_valid) {
-      float* g = dst + (long long)rr * ld + c;
-      if (atomic) {
-        atomicAdd(g, t.x);
-        if (c + 1 < cols_valid) atomicAdd(g + 1, t.y);
-        if (c + 2 < cols_valid) atomicAdd(g + 2, t.z);
-        if (c + 3 < cols_valid) atomicAdd(g + 3, t.w);
-      } else if (vec_ok && c + 4 <= cols_valid) {
-        *reinterpret_cast<float4*>(g) = t;
-      } else {
-        g[0] = t.x;
-        if (c + 1 < cols_valid) g[1] = t.y;
-        if (c + 2 < cols_valid) g[2] = t.z;
-        if (c + 3 < cols_valid) g[3] = t.w;
-      }
-    }
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void wt_load_f32(float* stg, float (&v)[32], const float* src, long long ld, int rows_valid,
-                                            int cols_valid, int lane) {
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld & 3) == 0);
-  const int s = lane & 7, c = s * 4;
-  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
-    float4 t[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) t[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)(it * 4 + (lane >> 3)) * ld + c));
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3);
-      *reinterpret_cast<float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2)) = t[it];
-    }
-  } else
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rr < rows_valid && c < cols_valid) {
-      const float* g = src + (long long)rr * ld + c;
-      if (vec_ok && c + 4 <= cols_valid) {
-        t = __ldg(reinterpret_cast<const float4*>(g));
-      } else {
-        t.x = g[0];
-        if (c + 1 < cols_valid) t.y = g[1];
-        if (c + 2 < cols_valid) t.z = g[2];
-        if (c + 3 < cols_valid) t.w = g[3];
-      }
-    }
-    *reinterpret_cast<float4*>(stg + rr * 32 + ((s ^ (rr & 7)) << 2)) = t;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2));
-    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-  }
-  __syncwarp();
-}
-// 32 rows x 32 bf16 (64-byte rows): 4 uint4 slots per row, slot' = slot ^ ((row >> 1) & 3)
-__device__ __forceinline__ void wt_store_bf16(float* stg_f, const uint32_t (&pk)[16], bf16* dst, long long ld, int rows_valid,
-                                              int cols_valid, int lane) {
-  uint4* stg = reinterpret_cast<uint4*>(stg_f);
-#pragma unroll
-  for (int s = 0; s < 4; ++s) stg[lane * 4 + (s ^ ((lane >> 1) & 3))] = make_uint4(pk[4 * s], pk[4 * s + 1], pk[4 * s + 2], pk[4 * s + 3]);
-  __syncwarp();
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((ld & 7) == 0);
-  const int s = lane & 3, c = s * 8;
-  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
-    uint4 t[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2);
-      t[it] = stg[rr * 4 + (s ^ ((rr >> 1) & 3))];
-    }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(dst + (long long)(it * 8 + (lane >> 2)) * ld + c) = t[it];
-    __syncwarp();
-    return;
-  }
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rr = it * 8 + (lane >> 2);
-    const uint4 t = stg[rr * 4 + (s ^ ((rr >> 1) & 3))];
-    if (rr < rows_valid && c < cols_valid) {
-      bf16* g = dst + (long long)rr * ld + c;
-      if (vec_ok && c + 8 <= cols_valid) {
-        *reinterpret_cast<uint4*>(g) = t;
-      } else {
-        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (c + k < cols_valid) g[k] = __ushort_as_bfloat16((unsigned short)((u[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu));
-      }
-    }
-  }
-  __syncwarp();
-}
-// returns a bit mask: bit j set <=> src[row = lane][col j] > 0
-__device__ __forceinline__ uint32_t wt_load_posmask_bf16(float* stg_f, const bf16* src, long long ld, int rows_valid,
-                                                        int cols_valid, int lane) {
-  uint4* stg = reinterpret_cast<uint4*>(stg_f);
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld & 7) == 0);
-  const int s = lane & 3, c = s * 8;
-  if (vec_ok && rows_valid == 32 && cols_valid == 32) {
-    uint4 t[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) t[it] = __ldg(reinterpret_cast<const uint4*>(src + (long long)(it * 8 + (lane >> 2)) * ld + c));
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2);
-      stg[rr * 4 + (s ^ ((rr >> 1) & 3))] = t[it];
-    }
-  } else
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rr = it * 8 + (lane >> 2);
-    uint4 t = make_uint4(0u, 0u, 0u, 0u);
-    if (rr < rows_valid && c < cols_valid) {
-      const bf16* g = src + (long long)rr * ld + c;
-      if (vec_ok && c + 8 <= cols_valid) {
-        t = __ldg(reinterpret_cast<const uint4*>(g));
-      } else {
-        uint32_t u[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (c + k < cols_valid) u[k >> 1] |= (uint32_t)__bfloat16_as_ushort(g[k]) << ((k & 1) * 16);
-        t = make_uint4(u[0], u[1], u[2], u[3]);
-      }
-    }
-    stg[rr * 4 + (s ^ ((rr >> 1) & 3))] = t;
-  }
-  __syncwarp();
-  uint32_t pos = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 t = stg[lane * 4 + (q ^ ((lane >> 1) & 3))];
-    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t lo = u[k] & 0xFFFFu, hi = u[k] >> 16;
-      if (lo != 0u && lo < 0x8000u) pos |= 1u << (q * 8 + 2 * k);
-      if (hi != 0u && hi < 0x8000u) pos |= 1u << (q * 8 + 2 * k + 1);
-    }
-  }
-  __syncwarp();
-  return pos;
-}
-
-// One 32-row x 32-column chunk of the epilogue for the warp owning TMEM lanes [quarter*32, +32).
-#define NRW_EPI_TICK(slot)                                                     \
-  if (pc) {                                                                    \
-    const long long _now = clock64();                                          \
-    atomicAdd(&pc[slot], (unsigned long long)(_now - _tick));                  \
-    _tick = _now;                                                              \
-  }
-__device__ __forceinline__ void epi_chunk(const Epi& e, float* stg, float (&acc)[32], int m0w, int nc, int M, int N, int lane,
-                                          unsigned long long* pc) {
-  const int rows_valid = min(32, M - m0w);
-  if (rows_valid <= 0) return;
-  long long _tick = pc ? clock64() : 0;
-  const int n_all = min(N - nc, 32);
-  const int n_st = min(e.n_store - nc, n_all);
-  const int m = min(m0w + lane, M - 1);
-  epi_bias<32>(e, m, nc, n_all, acc);
-  if (e.out_pre) wt_store_f32(stg, acc, e.out_pre + (long long)m0w * e.ld_pre + nc, e.ld_pre, rows_valid, n_all, lane, false);
-  NRW_EPI_TICK(9);
-  if (n_st <= 0) return;
-  if (e.atomic) {
-    if (e.scale != 1.0f) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] *= e.scale;
-    }
-    wt_store_f32(stg, acc, e.out_f32 + (long long)m0w * e.ld_f32 + nc, e.ld_f32, rows_valid, n_st, lane, true);
-    return;
-  }
-  float a[32], q[32], ad[32], w[32];
-  uint32_t pos = 0;
-  if (e.aux_sig) wt_load_f32(stg, a, e.aux_sig + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
-  if (e.out2) {
-    if (e.aux_q_bcast) load_f32<32>(e.aux_q + nc, n_st, q);
-    else wt_load_f32(stg, q, e.aux_q + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
-  }
-  if (e.aux_add) wt_load_f32(stg, ad, e.aux_add + (long long)m0w * e.ld_aux + nc, e.ld_aux, rows_valid, n_st, lane);
-  if (e.aux_relu) pos = wt_load_posmask_bf16(stg, e.aux_relu + (long long)m0w * e.ld_relu + nc, e.ld_relu, rows_valid, n_st, lane);
-  NRW_EPI_TICK(10);
-  epi_math<32>(e, acc, a, q, ad, pos, w);
-  NRW_EPI_TICK(11);
-  if (e.colsum) {
-    // column sums of the 32x32 tile through the staging buffer: lane j owns column j (conflict-free reads)
-#pragma unroll
-    for (int s = 0; s < 8; ++s)
-      *reinterpret_cast<float4*>(stg + lane * 32 + ((s ^ (lane & 7)) << 2)) = make_float4(w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
-    __syncwarp();
-    float cs = 0.0f;
-    for (int r = 0; r < rows_valid; ++r) cs += stg[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
-    if (lane < n_st) atomicAdd(e.colsum + nc + lane, cs);
-    __syncwarp();
-  }
-  if (e.out2) wt_store_f32(stg, q, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, rows_valid, n_st, lane, false);
-  if (e.out_f32) wt_store_f32(stg, w, e.out_f32 + (long long)m0w * e.ld_f32 + nc, e.ld_f32, rows_valid, n_st, lane, false);
-  for (int pl = 0; pl < e.n_planes; ++pl) {
-    uint32_t pk[16];
-    split_plane<32>(w, pk);
-    wt_store_bf16(stg, pk, e.out_pl.plane(pl) + (long long)m0w * e.out_pl.ld + nc, e.out_pl.ld, rows_valid, n_st, lane);
-  }
-  NRW_EPI_TICK(12);
 }
 
 template <int BN, int MN_MAJOR>
@@ -447,6 +207,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256 + STG_BYTES);
+  if (threadIdx.x < 256) cs_buf[threadIdx.x] = 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -554,15 +316,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                // column interleave among warps of the same quarter
     constexpr int CH_PER = N_EPI_WARPS / 4;   // warps per quarter
-    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 1024;
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
+    const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
+    const int etid = threadIdx.x - 128;
+    int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
       const int n0 = (t % p.n_tiles) * BN, m0 = (t / p.n_tiles) * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
       const bool prof = p.prof != nullptr && warp == 4 && lane == 0;
+      if (use_cs && n0 != cs_n0) {
+        if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN), etid, 32 * N_EPI_WARPS, 1);
+        cs_n0 = n0;
+      }
       {
         NRW_PROF_T0(prof);
         mbar_wait(bar_tfull + 8 * acc, acc_ph);
@@ -572,16 +341,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       {
         NRW_PROF_T0(prof);
         if (kb1 > kb0) {
-          for (int c = chalf; c < BN / 32; c += CH_PER) {
-            const int nc = n0 + c * 32;
+          for (int c = chalf; c < BN / 16; c += CH_PER) {
+            const int nc = n0 + c * 16;
             if (nc >= p.N) break;               // warp-uniform
-            float v[32];
+            float v[16];
             {
               NRW_PROF_T0(prof);
-              tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+              tmem_ld16(tmem_base + acc * BN + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
               NRW_PROF_ADD(prof, 8);
             }
-            epi_chunk(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, prof ? p.prof + blockIdx.x * 16 : nullptr);
+            epi_chunk16(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
           }
         }
         tc_fence_before();
@@ -592,6 +361,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (use_cs && cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN), etid, 32 * N_EPI_WARPS, 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -693,6 +463,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256 + STG_BYTES);
+  if (threadIdx.x < 256) cs_buf[threadIdx.x] = 0.0f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -704,6 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
   const int n_items = p.m_tiles * p.n_tiles * p.k_slices;   // m_tiles counts 256-row tiles
   const int n_prod = (P == 1) ? 1 : (P == 2 ? 3 : 6);
   const int unit = blockIdx.x >> 1, n_units = gridDim.x >> 1;
+  const long long t_kernel0 = p.prof ? clock64() : 0;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -717,7 +490,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
         const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          {
+            NRW_PROF_T0(p.prof != nullptr);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            NRW_PROF_ADD(p.prof != nullptr, 0);
+          }
           if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
           const uint32_t bfl = (bar_full + 8 * s) & PEER_MASK;
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
@@ -751,12 +528,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
       for (int item = unit; item < n_items; item += n_units) {
         const int ks = item % p.k_slices;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+        {
+          NRW_PROF_T0(p.prof != nullptr);
+          mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+          NRW_PROF_ADD(p.prof != nullptr, 2);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
         uint32_t first = 1;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
+          {
+            NRW_PROF_T0(p.prof != nullptr);
+            mbar_wait(bar_full + 8 * s, ph);
+            NRW_PROF_ADD(p.prof != nullptr, 1);
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + P * A_TILE;
@@ -767,6 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
             const uint64_t db = make_sdesc(sb + pb * B_TILE, LBO, SBO);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
+              if ((p.dbg & 2) && (pr | k)) continue;
               umma_bf16_2sm(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -784,35 +570,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     const int quarter = warp & 3;
     const int chalf = ew >> 2;
     constexpr int CH_PER = N_EPI_WARPS / 4;
-    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 1024;
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
+    const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
+    const int etid = threadIdx.x - 128;
+    int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
       const int n0 = (t % p.n_tiles) * BN2;
       const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
-      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      if (use_cs && n0 != cs_n0) {
+        if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
+        cs_n0 = n0;
+      }
+      const bool prof = p.prof != nullptr && warp == 4 && lane == 0;
+      {
+        NRW_PROF_T0(prof);
+        mbar_wait(bar_tfull + 8 * acc, acc_ph);
+        NRW_PROF_ADD(prof, 3);
+      }
       tc_fence_after();
+      NRW_PROF_T0(prof);
+      if (prof) atomicAdd(&p.prof[blockIdx.x * 16 + 6], 1ull);
       if (kb1 > kb0) {
-        for (int c = chalf; c < BN2 / 32; c += CH_PER) {
-          const int nc = n0 + c * 32;
+        for (int c = chalf; c < BN2 / 16; c += CH_PER) {
+          const int nc = n0 + c * 16;
           if (nc >= p.N) break;
-          float v[32];
-          tmem_ld32(tmem_base + acc * BN2 + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
-          epi_chunk(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, nullptr);
+          float v[16];
+          tmem_ld16(tmem_base + acc * BN2 + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
+          if (!(p.dbg & 1)) epi_chunk16(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
         }
       }
       tc_fence_before();
       __syncwarp();
+      NRW_PROF_ADD(prof, 4);
       if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (use_cs && cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // the peer may still signal our barriers / read our shared memory until here
+  if (p.prof && threadIdx.x == 0) atomicAdd(&p.prof[blockIdx.x * 16 + 5], (unsigned long long)(clock64() - t_kernel0));
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -909,7 +712,7 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
 static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream);
 
 // ---- live kernel timing (bench.py roofline): CUDA events around every launch on the launching stream ----
-struct TimedLaunch { cudaEvent_t e0, e1; double flops; double mma_flops; };
+struct TimedLaunch { cudaEvent_t e0, e1; double flops; double mma_flops; int M, N, K, P, mn, ks; unsigned epi; double bytes; };
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
 static bool g_timing_on = false;
@@ -923,13 +726,18 @@ static cudaEvent_t get_event() {
 // sums (and clears) the recorded launches: total kernel ms, algorithmic FLOP (2MNK), MMA FLOP (x products), count
 int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches) {
   double t = 0, f = 0, mf = 0;
+  // tuning: NRW_GEMM_TIMING_DUMP=<path> appends one CSV row per launch: M,N,K,planes,mn_major,k_slices,epilogue bits,
+  // algorithmic bytes,ms   (bits: 1 out_pre 2 out_f32 4 out2 8 planes 16 aux_sig 32 aux_q 64 aux_add 128 aux_relu 256 atomic 512 colsum)
+  FILE* dump = getenv("NRW_GEMM_TIMING_DUMP") ? fopen(getenv("NRW_GEMM_TIMING_DUMP"), "a") : nullptr;
   for (auto& L : g_timed) {
     NRW_CUDA_OK(cudaEventSynchronize(L.e1));
     float dt = 0;
     NRW_CUDA_OK(cudaEventElapsedTime(&dt, L.e0, L.e1));
     t += dt; f += L.flops; mf += L.mma_flops;
     g_event_pool.push_back(L.e0); g_event_pool.push_back(L.e1);
+    if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%u,%.0f,%.4f\n", L.M, L.N, L.K, L.P, L.mn, L.ks, L.epi, L.bytes, dt);
   }
+  if (dump) fclose(dump);
   *ms = t; *flops = f; *mma_flops = mf; *launches = (long long)g_timed.size();
   g_timed.clear();
   return NRW_OK;
@@ -941,6 +749,15 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   L.e0 = get_event(); L.e1 = get_event();
   L.flops = 2.0 * g.M * g.N * g.K;
   L.mma_flops = L.flops * n_products(g.n_planes);
+  L.M = g.M; L.N = g.N; L.K = g.K; L.P = g.n_planes; L.mn = g.mn_major; L.ks = g.k_slices;
+  const Epi& e = g.epi;
+  L.epi = (e.out_pre ? 1u : 0u) | (e.out_f32 ? 2u : 0u) | (e.out2 ? 4u : 0u) | (e.n_planes ? 8u : 0u) | (e.aux_sig ? 16u : 0u) |
+          ((e.aux_q && !e.aux_q_bcast) ? 32u : 0u) | (e.aux_add ? 64u : 0u) | (e.aux_relu ? 128u : 0u) | (e.atomic ? 256u : 0u) |
+          (e.colsum ? 512u : 0u);
+  const double mn = (double)g.M * (double)std::min(g.N, e.n_store);
+  L.bytes = 2.0 * g.n_planes * ((double)g.M * g.K + (double)g.N * g.K) + (e.out_pre ? 4.0 * g.M * g.N : 0.0) +
+            mn * (4.0 * ((e.out_f32 ? 1 : 0) + (e.out2 ? 1 : 0) + (e.aux_sig ? 1 : 0) + ((e.aux_q && !e.aux_q_bcast) ? 1 : 0) +
+                         (e.aux_add ? 1 : 0)) + 2.0 * e.n_planes + (e.aux_relu ? 2.0 : 0.0));
   NRW_CUDA_OK(cudaEventRecord(L.e0, stream));
   const int rc = gemm_tc_impl(g, stream);
   NRW_CUDA_OK(cudaEventRecord(L.e1, stream));
@@ -970,6 +787,8 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   p.m_tiles = cdiv(g.M, BM); p.n_tiles = cdiv(g.N, BN);
   p.epi = g.epi;
   p.prof = g_prof_ptr;
+  static const int dbg = getenv("NRW_TC_DBG") ? atoi(getenv("NRW_TC_DBG")) : 0;
+  p.dbg = dbg;
   // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) for the wide layers
   static const int use_2cta = getenv("NRW_TC_2CTA") ? atoi(getenv("NRW_TC_2CTA")) : 1;
   if (use_2cta && g.N >= 256 && g.M >= 256) {
