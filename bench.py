@@ -263,16 +263,29 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     # e2e: host buffers, H2D of the batch + D2H of the loss inside the timed region
     run(1, True)
+    clocks2 = ClockSampler(local)
+    if rank == 0:
+        clocks2.start()
     barrier()
     e0.record()
     run(args.steps, True)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    clk2 = clocks2.stop() if rank == 0 else None
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- roofline of the dominant kernel: CUDA events around EVERY tcgen05 GEMM launch of two more steps.
+    # Every rank runs them (the step holds the gradient all-reduce); only rank 0's kernel times are reported. ----
+    import ctypes as C
+    L.nrw_gemm_timing(1, None)
+    run(2, False)
+    torch.cuda.synchronize()
+    out4 = (C.c_double * 4)()
+    L.nrw_gemm_timing(0, out4)
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -282,13 +295,6 @@ def main():
     peak_tf, peak_hbm, peak_src = peaks()
     DTYPES = {"bf16": "bf16", "bf16x3": "bf16 (3-product split, fp32 accumulate)", "bf16x6": "bf16 (6-product split, fp32 accumulate)",
               "mixed": "bf16 (3-product split forward, plain bf16 backward, fp32 accumulate)"}
-    # ---- roofline of the dominant kernel: CUDA events around EVERY tcgen05 GEMM launch of two more steps ----
-    import ctypes as C
-    L.nrw_gemm_timing(1, None)
-    run(2, False)
-    torch.cuda.synchronize()
-    out4 = (C.c_double * 4)()
-    L.nrw_gemm_timing(0, out4)
     k_ms, k_flop, k_mma, k_n = out4[0] / 2, out4[1] / 2, out4[2] / 2, out4[3] / 2
     achieved_tf = k_flop / (k_ms * 1e-3) / 1e12
     traffic = None
@@ -301,7 +307,7 @@ def main():
             "data": "synthetic", "config": config, "precision_mode": args.precision, "loss": float(loss),
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "clocks": clk2},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 GEMM of every dense layer)",

@@ -128,6 +128,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// one lane of the (converged) warp, the same one every time
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -160,15 +172,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int mn_major) {
 }
 
 // product p of the plane expansion -> (a_plane, b_plane); ordered small-to-large magnitude last
-__device__ __forceinline__ void product_planes(int n_planes, int p, int& pa, int& pb) {
-  // n_planes==1: (0,0); ==2: (0,1),(1,0),(0,0); ==3: (0,2),(2,0),(1,1),(0,1),(1,0),(0,0)
-  const int np = (n_planes == 1) ? 1 : (n_planes == 2 ? 3 : 6);
-  const int q = np - 1 - p;  // q=0 is (0,0)
-  const int ta[6] = {0, 1, 0, 1, 2, 0};
-  const int tb[6] = {0, 0, 1, 1, 0, 2};
-  pa = ta[q];
-  pb = tb[q];
-}
+//   n_planes==1: (0,0); ==2: (0,1),(1,0),(0,0); ==3: (0,2),(2,0),(1,1),(0,1),(1,0),(0,0)
+// With q = n_products-1-p (q=0 is (hi,hi)): a_plane = nibble q of 0x021010, b_plane = nibble q of 0x201100.
 
 template <int BN, int MN_MAJOR>
 __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
@@ -176,7 +181,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   constexpr int B_TILE = BN * BK * 2;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages (power of 2)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window by OFFSET (an integer round trip of the pointer would turn every staging access
+  // into a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
   int stages = STAGE_BUDGET / stage_bytes;
@@ -259,7 +266,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // whole warp, one elected issuing lane (see the CTA-pair kernel below)
+      const bool issuer = elect_one();
+      const bool prof_m = p.prof != nullptr && lane == 0;
+      const uint32_t smem0 = smem_u32(smem);
       constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR);
       // K-major: SBO = 8 rows * 128 B; MN-major: LBO = stride between 64-wide MN slabs, SBO = 8 k-rows
       constexpr uint32_t LBO = MN_MAJOR ? (64 * BK * 2) : 16;
@@ -271,42 +281,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int ks = item % p.k_slices;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         {
-          NRW_PROF_T0(p.prof != nullptr);
+          NRW_PROF_T0(prof_m);
           mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
-          NRW_PROF_ADD(p.prof != nullptr, 2);
+          NRW_PROF_ADD(prof_m, 2);
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t first = 1;
+        uint32_t accum = 0;
+        const uint64_t desc_hi = make_sdesc(0, LBO, SBO);   // everything but the start address
         for (int kb = kb0; kb < kb1; ++kb) {
           {
-            NRW_PROF_T0(p.prof != nullptr);
+            NRW_PROF_T0(prof_m);
             mbar_wait(bar_full + 8 * s, ph);
-            NRW_PROF_ADD(p.prof != nullptr, 1);
+            NRW_PROF_ADD(prof_m, 1);
           }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sa = smem0 + s * stage_bytes;
           const uint32_t sb = sa + P * A_TILE;
-          for (int pr = 0; pr < n_prod; ++pr) {
-            int pa, pb;
-            product_planes(P, pr, pa, pb);
-            const uint64_t da = make_sdesc(sa + pa * A_TILE, LBO, SBO);
-            const uint64_t db = make_sdesc(sb + pb * B_TILE, LBO, SBO);
+          if (issuer) {
+            for (int pr = 0; pr < n_prod; ++pr) {
+              const int q = 4 * (n_prod - 1 - pr);           // product order of product_planes(), packed lookup
+              const uint32_t pa = (0x021010u >> q) & 0xFu, pb = (0x201100u >> q) & 0xFu;
+              const uint64_t da = desc_hi | (uint64_t)(((sa + pa * A_TILE) & 0x3FFFFu) >> 4);
+              const uint64_t db = desc_hi | (uint64_t)(((sb + pb * B_TILE) & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, first ? 0u : 1u);
-              first = 0;
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, accum);
+                accum = 1;
+              }
             }
+            umma_commit(bar_empty + 8 * s);
           }
-          umma_commit(bar_empty + 8 * s);
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        if (kb1 > kb0) {
-          umma_commit(bar_tfull + 8 * acc);
-        } else {
-          // empty slice: nothing accumulated; still hand the (stale) stage over so roles stay in step
-          umma_commit(bar_tfull + 8 * acc);
-        }
+        // (an empty k-slice accumulates nothing but still hands the stage over so the roles stay in step)
+        if (issuer) umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -427,7 +438,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
   constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
   constexpr int TMEM_COLS = 2 * BN2;               // two 256-column accumulators
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window by OFFSET (an integer round trip of the pointer would turn every staging access
+  // into a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
   int stages = STAGE_BUDGET / stage_bytes;
@@ -517,50 +530,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // The WHOLE warp walks the loop (warp-uniform control flow and addresses, so descriptors live in uniform
+    // registers) and one elected lane issues the tcgen05 instructions; a single-lane divergent region made the
+    // compiler wrap every MMA in a register->uniform-register "waterfall" loop and starved the issue slot.
+    if (leader) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MN_MAJOR << 15) | ((uint32_t)MN_MAJOR << 16) |
                                  ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
       constexpr uint32_t LBO = MN_MAJOR ? (64 * BK * 2) : 16;
       constexpr uint32_t SBO = 1024;
       constexpr uint32_t KSTEP = MN_MAJOR ? (16 * 128) : 32;
+      const uint64_t desc_hi = make_sdesc(0, LBO, SBO);          // everything but the start address
+      const uint32_t smem0 = smem_u32(smem);
+      const bool issuer = elect_one();
+      const bool prof_m = p.prof != nullptr && lane == 0;
       int s = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0;
       for (int item = unit; item < n_items; item += n_units) {
         const int ks = item % p.k_slices;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         {
-          NRW_PROF_T0(p.prof != nullptr);
+          NRW_PROF_T0(prof_m);
           mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
-          NRW_PROF_ADD(p.prof != nullptr, 2);
+          NRW_PROF_ADD(prof_m, 2);
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
-        uint32_t first = 1;
+        uint32_t accum = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           {
-            NRW_PROF_T0(p.prof != nullptr);
+            NRW_PROF_T0(prof_m);
             mbar_wait(bar_full + 8 * s, ph);
-            NRW_PROF_ADD(p.prof != nullptr, 1);
+            NRW_PROF_ADD(prof_m, 1);
           }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sa = smem0 + s * stage_bytes;
           const uint32_t sb = sa + P * A_TILE;
-          for (int pr = 0; pr < n_prod; ++pr) {
-            int pa, pb;
-            product_planes(P, pr, pa, pb);
-            const uint64_t da = make_sdesc(sa + pa * A_TILE, LBO, SBO);
-            const uint64_t db = make_sdesc(sb + pb * B_TILE, LBO, SBO);
+          if (issuer) {
+            for (int pr = 0; pr < n_prod; ++pr) {
+              // product order: smallest magnitude first, (hi,hi) last; packed lookup (no local-memory tables)
+              const int q = 4 * (n_prod - 1 - pr);
+              const uint32_t pa = (0x021010u >> q) & 0xFu, pb = (0x201100u >> q) & 0xFu;
+              const uint64_t da = desc_hi | (uint64_t)(((sa + pa * A_TILE) & 0x3FFFFu) >> 4);
+              const uint64_t db = desc_hi | (uint64_t)(((sb + pb * B_TILE) & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if ((p.dbg & 2) && (pr | k)) continue;
-              umma_bf16_2sm(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, first ? 0u : 1u);
-              first = 0;
+              for (int k = 0; k < BK / 16; ++k) {
+                if ((p.dbg & 2) && (pr | k)) continue;
+                umma_bf16_2sm(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, accum);
+                accum = 1;
+              }
             }
+            umma_commit_2sm(bar_empty + 8 * s);
           }
-          umma_commit_2sm(bar_empty + 8 * s);
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(bar_tfull + 8 * acc);
+        if (issuer) umma_commit_2sm(bar_tfull + 8 * acc);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
