@@ -305,6 +305,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision],
             "data": "synthetic", "config": config, "precision_mode": args.precision, "loss": float(loss),
+            "forward_slots": list(getattr(sysm.renderer.engine, "slots", ())),
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "clocks": clk2},
@@ -341,7 +342,8 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     m = e0.elapsed_time(e1) / args.steps
-                    others[mode] = {"value": R / (m * 1e-3), "unit": "rays/s", "ms_per_step": m, "dtype": DTYPES[mode]}
+                    others[mode] = {"value": R / (m * 1e-3), "unit": "rays/s", "ms_per_step": m, "dtype": DTYPES[mode],
+                                    "forward_slots": list(getattr(sysm.renderer.engine, "slots", ()))}
                 except Exception as e:  # noqa
                     others[mode] = {"error": str(e)[:200]}
             line["other_precision_modes"] = others

@@ -493,7 +493,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {   // whole warp walks the loop (uniform addresses), one elected lane issues
+      const bool issuer = elect_one();
+      const bool prof_p = p.prof != nullptr && lane == 0;
+      const uint32_t smem0 = smem_u32(smem);
       int s = 0;
       uint32_t ph = 0;
       for (int item = unit; item < n_items; item += n_units) {
@@ -504,26 +507,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           {
-            NRW_PROF_T0(p.prof != nullptr);
+            NRW_PROF_T0(prof_p);
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            NRW_PROF_ADD(p.prof != nullptr, 0);
+            NRW_PROF_ADD(prof_p, 0);
           }
-          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
-          const uint32_t bfl = (bar_full + 8 * s) & PEER_MASK;
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint32_t sb = sa + P * A_TILE;
-          for (int pl = 0; pl < P; ++pl) {
-            if (MN_MAJOR == 0) {
-              tma_load_2d_2sm(sa + pl * A_TILE, &p.tmA[pl], bfl, kb * BK, m0);
-              tma_load_2d_2sm(sb + pl * B_TILE, &p.tmB[pl], bfl, kb * BK, n0);
-            } else {
+          if (issuer) {
+            if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
+            const uint32_t bfl = (bar_full + 8 * s) & PEER_MASK;
+            const uint32_t sa = smem0 + s * stage_bytes;
+            const uint32_t sb = sa + P * A_TILE;
+            for (int pl = 0; pl < P; ++pl) {
+              if (MN_MAJOR == 0) {
+                tma_load_2d_2sm(sa + pl * A_TILE, &p.tmA[pl], bfl, kb * BK, m0);
+                tma_load_2d_2sm(sb + pl * B_TILE, &p.tmB[pl], bfl, kb * BK, n0);
+              } else {
 #pragma unroll
-              for (int sl = 0; sl < 2; ++sl) {
-                tma_load_2d_2sm(sa + pl * A_TILE + sl * (64 * BK * 2), &p.tmA[pl], bfl, m0 + 64 * sl, kb * BK);
-                tma_load_2d_2sm(sb + pl * B_TILE + sl * (64 * BK * 2), &p.tmB[pl], bfl, n0 + 64 * sl, kb * BK);
+                for (int sl = 0; sl < 2; ++sl) {
+                  tma_load_2d_2sm(sa + pl * A_TILE + sl * (64 * BK * 2), &p.tmA[pl], bfl, m0 + 64 * sl, kb * BK);
+                  tma_load_2d_2sm(sb + pl * B_TILE + sl * (64 * BK * 2), &p.tmB[pl], bfl, n0 + 64 * sl, kb * BK);
+                }
               }
             }
           }
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
