@@ -200,6 +200,20 @@ NRW_API int nrw_octree_hits(const uint8_t* octree, const int32_t* prefix, const 
                             const float scene_origin[3], float scale, const int64_t* offsets,
                             int32_t* ray_index, int32_t* point_index, float* depth, void* stream);
 
+/* ---- octree build (K0; tools/prepare_data/generate_voxel.py:149-150 quantize_points + unbatched_points_to_octree,
+ *      :173-178 scan_octrees + generate_points; called by get_octree renderer.py:137-155 and octree_update
+ *      neuconw_system.py:268-312) ------------------------------------------------------------------------------- */
+/* points [n,3] (float32, or float64 when points_are_f64) already normalised to the open cube (-1,1)
+ * (generate_voxel.py:113-127).  Device outputs: octree uint8 [cap_nonleaf] (breadth-first child masks, zero padded),
+ * prefix int32 [cap_nonleaf] (exclusive popcount sum), pyramid int32 [2, level+2], points_out int16 [cap_total,3]
+ * (node coordinates of every level, breadth-first), counts_out int32 [2] = {#non-leaf nodes, #nodes}.  Nothing is
+ * written out of bounds when a capacity is too small: compare counts_out with the capacities after synchronising
+ * (n_points * level / n_points * (level+1) always suffice).  scratch: nrw_octree_build_scratch_bytes, 256-byte aligned. */
+NRW_API long long nrw_octree_build_scratch_bytes(int n_points, int level, int cap_nonleaf);
+NRW_API int nrw_octree_build(const void* points, int points_are_f64, int n_points, int level, uint8_t* octree,
+                             int32_t* prefix, int32_t* pyramid, int16_t* points_out, int cap_nonleaf, int cap_total,
+                             int32_t* counts_out, void* scratch, void* stream);
+
 /* ---- unit-test hooks ---------------------------------------------------------------------- */
 /* D[M,N] = (sum planes of A)[M,K] * (sum planes of B)[N,K]^T from fp32 inputs: splits into planes in
  * scratch (caller-provided, nrw_gemm_test_scratch_bytes) and runs the selected backend. */

@@ -236,6 +236,20 @@ int nrw_octree_hits(const uint8_t* octree, const int32_t* prefix, const int32_t*
   NRW_GUARD_END
 }
 
+long long nrw_octree_build_scratch_bytes(int n_points, int level, int cap_nonleaf) {
+  return octree_build_scratch_bytes(n_points, level, cap_nonleaf);
+}
+int nrw_octree_build(const void* points, int points_are_f64, int n_points, int level, uint8_t* octree, int32_t* prefix,
+                     int32_t* pyramid, int16_t* points_out, int cap_nonleaf, int cap_total, int32_t* counts_out,
+                     void* scratch, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(octree && prefix && pyramid && points_out && counts_out && scratch, NRW_ERR_ARG, "nrw_octree_build: null output");
+  NRW_CHECK(n_points == 0 || points, NRW_ERR_ARG, "nrw_octree_build: null points");
+  return octree_build(points, points_are_f64, n_points, level, octree, prefix, pyramid, points_out, cap_nonleaf, cap_total,
+                      counts_out, scratch, S(stream));
+  NRW_GUARD_END
+}
+
 long long nrw_gemm_test_scratch_bytes(int M, int N, int K) {
   const long long a = round_up((long long)M * K, 512), b = round_up((long long)N * K, 512);
   return (a + b) * 3 * 2 + 4096;

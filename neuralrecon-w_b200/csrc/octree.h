@@ -10,3 +10,10 @@ int octree_hits(const uint8_t* octree, const int32_t* prefix, const int32_t* pyr
                 const float* rays_o, const float* rays_d, int R, const float scene_origin[3], float scale,
                 const int64_t* offsets, int32_t* ray_index, int32_t* point_index, float* depth, cudaStream_t s);
 }  // namespace nrw
+
+// K0: octree builder (octree_build.cu)
+namespace nrw {
+long long octree_build_scratch_bytes(int n_points, int level, int cap_nonleaf);
+int octree_build(const void* points, int is_f64, int n, int level, uint8_t* octree, int32_t* prefix, int32_t* pyramid,
+                 int16_t* points_out, int cap_nonleaf, int cap_total, int32_t* counts_out, void* scratch, cudaStream_t s);
+}  // namespace nrw

@@ -64,8 +64,17 @@ class NeuconWRenderer:
 
     # ------------------------------------------------------------------------------------------------
     def get_octree(self, device):
-        raise NrwError("get_octree: building the SfM octree from COLMAP points is outside the accelerated "
-                       "path; assign renderer.octree_data (keys octree, scene_origin, scale, level, spc_data)")
+        """renderer.py:137-155.  Reading COLMAP's points3D.bin / the scene's config.yaml is data loading and stays
+        with the caller: set `renderer.sfm_points` ([P,3], track-length filtered, generate_voxel.py:56-61) and
+        `renderer.scene_config` (dict with sfm2gt, eval_bbx); the octree itself is built on the GPU (K0)."""
+        pts = getattr(self, "sfm_points", None)
+        cfg = getattr(self, "scene_config", None)
+        if pts is None or cfg is None:
+            raise NrwError("get_octree: set renderer.sfm_points ([P,3] SfM points) and renderer.scene_config "
+                           "(sfm2gt, eval_bbx), or assign renderer.octree_data directly "
+                           "(keys octree, scene_origin, scale, level, spc_data)")
+        from .octree import make_octree_data
+        return make_octree_data(cfg, pts, self.voxel_size, device=device)
 
     def _octree_near_far(self, od, rays_o_sfm, rays_d):
         """get_near_far (tools/prepare_data/generate_voxel.py:311-439) on the CUDA octree tracer."""

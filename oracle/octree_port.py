@@ -134,3 +134,35 @@ def sphere_shell_points(radius=0.5, voxel=0.05, seed=0, n=20000):
     v = rng.randn(n, 3)
     v /= np.linalg.norm(v, axis=1, keepdims=True)
     return v * (radius + (rng.rand(n, 1) * 2 - 1) * voxel)
+
+
+# ---- K0 host math around the builder (tools/prepare_data/generate_voxel.py:27-38, 75-150) -------------------------
+def expand_points(points, voxel_size):
+    """generate_voxel.py:27-38: 3x3x3 dilation by voxel_size, unique rows."""
+    from itertools import product
+    grids = list(product(*zip([-1, -1, -1], [0, 0, 0], [1, 1, 1])))
+    ex = np.concatenate([points + np.array(g) * voxel_size for g in grids], axis=0)
+    return np.unique(ex, axis=0)
+
+
+def gen_octree(scene_config, points, voxel_size, expand=1, radius=1.0, in_sfm=True):
+    """generate_voxel.py:75-150 without file I/O (scene_config = the dict read from config.yaml).
+    Returns (tree, scene_origin, scale, level, points_filtered)."""
+    points = np.asarray(points, np.float64)
+    if in_sfm:
+        gt_to_sfm = np.linalg.inv(np.array(scene_config["sfm2gt"]))
+        v1 = gt_to_sfm[:3, :3] @ np.array(scene_config["eval_bbx"][0]) + gt_to_sfm[:3, 3]
+        v2 = gt_to_sfm[:3, :3] @ np.array(scene_config["eval_bbx"][1]) + gt_to_sfm[:3, 3]
+        bbx_min, bbx_max = np.minimum(v1, v2), np.maximum(v1, v2)
+    else:
+        bbx_min, bbx_max = np.array(scene_config["eval_bbx"][0]), np.array(scene_config["eval_bbx"][1])
+    dim = np.max(bbx_max - bbx_min)
+    for _ in range(expand):
+        points = expand_points(points, voxel_size)
+    scene_origin = bbx_min + (bbx_max - bbx_min) / 2
+    scale = dim / 2 * radius
+    pn = (points - scene_origin) / scale
+    mask = np.prod((pn > -1), axis=-1, dtype=bool) & np.prod((pn < 1), axis=-1, dtype=bool)
+    pf = pn[mask]
+    level = int(np.floor(np.log2(2 * scale / voxel_size)))
+    return build_octree(pf, level), scene_origin, scale, level, pf
