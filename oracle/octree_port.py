@@ -166,3 +166,37 @@ def gen_octree(scene_config, points, voxel_size, expand=1, radius=1.0, in_sfm=Tr
     pf = pn[mask]
     level = int(np.floor(np.log2(2 * scale / voxel_size)))
     return build_octree(pf, level), scene_origin, scale, level, pf
+
+
+# ---- octree refresh (lightning_modules/neuconw_system.py:186-312) ---------------------------------------------------
+def surface_selection(tree, octree_origin, octree_scale, octree_level, train_level, threshold, sdf_fn, scene_origin_sfm,
+                      scene_radius_sfm):
+    """neuconw_system.py:186-266 in the reference's dtypes: candidate voxels = every level-`octree_level` leaf split
+    2^(train_level-octree_level) times per axis; kept where sdf_fn(xyz_training float32 [n,3]) <= threshold.
+    Returns (sparse_pc_sfm float32 [m,3], train_voxel_size)."""
+    import torch
+    leaves = tree["levels"][octree_level]
+    order = np.lexsort((leaves[:, 2], leaves[:, 1], leaves[:, 0]))          # torch.nonzero(dense) order
+    sparse_ind = torch.from_numpy(leaves[order].astype(np.int64))
+    sparse_num = sparse_ind.shape[0]
+    up_times = 2 ** (train_level - octree_level)
+    sparse_ind_up = sparse_ind.repeat_interleave(up_times ** 3, dim=0) * up_times
+    k = torch.arange(0, up_times, 1)
+    up_kernal = torch.stack(torch.meshgrid(k, k, k, indexing="ij"), dim=-1).reshape(-1, 3)
+    sparse_ind_up = sparse_ind_up + up_kernal.repeat([sparse_num, 1])
+    train_voxel_size = 2 / (2 ** train_level) * octree_scale
+    origin32 = torch.as_tensor(np.asarray(octree_origin)).float()
+    vol_origin = origin32 - octree_scale
+    xyz_sfm = sparse_ind_up * train_voxel_size + vol_origin                   # float32
+    xyz_training = (xyz_sfm - torch.as_tensor(np.asarray(scene_origin_sfm)).float()) / scene_radius_sfm
+    sdf = np.asarray(sdf_fn(xyz_training.numpy()), np.float32).reshape(-1)
+    return xyz_sfm.numpy()[sdf <= threshold], train_voxel_size
+
+
+def octree_update(scene_config, tree, octree_origin, octree_scale, octree_level, train_level, threshold, sdf_fn,
+                  scene_origin_sfm, scene_radius_sfm):
+    """neuconw_system.py:268-312: surface_selection + gen_octree(expand=False)."""
+    pc, tvs = surface_selection(tree, octree_origin, octree_scale, octree_level, train_level, threshold, sdf_fn,
+                                scene_origin_sfm, scene_radius_sfm)
+    new_tree, origin, scale, level, _ = gen_octree(scene_config, pc, tvs, expand=0)
+    return new_tree, origin, scale, level, tvs, pc

@@ -100,3 +100,56 @@ def test_gen_octree_pipeline_and_trace():
     assert np.array_equal(cnt.cpu().numpy(), rc) and np.array_equal(pid.cpu().numpy(), rp)
     assert np.array_equal(near.cpu().numpy(), rn) and np.array_equal(far.cpu().numpy(), rf)
     assert (rc > 0).sum() > 20
+
+
+def test_octree_refresh_matches_restatement():
+    """neuconw_system.py:186-312 (surface_selection + octree_update) with an injected analytic SDF so that both sides
+    threshold identical float32 values: candidate generation, dtypes, filtering and the rebuilt octree are bit-exact."""
+    nrw = nrw_pkg()
+    from util_nrw import build_system, synth
+    cfg_scene = {"sfm2gt": np.eye(4).tolist(), "eval_bbx": [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]]}
+    pts = op.sphere_shell_points(0.55, 0.03, n=4000, seed=11)
+    voxel = 0.12
+    ref_tree, ref_origin, ref_scale, ref_level, _ = op.gen_octree(cfg_scene, pts, voxel, expand=1)
+    pc = synth.PathConfig(n_samples=8, n_importance=8, up_sample_steps=1, n_outside=0)
+    r = build_system(synth.make_params(seed=0), pc)["renderer"]
+    r.scene_config, r.sfm_points, r.voxel_size = cfg_scene, pts, voxel
+    r.octree_data = r.get_octree(0)
+    assert r.octree_data["level"] == ref_level
+    origin_sfm, radius_sfm = np.asarray(r.origin.cpu() if torch.is_tensor(r.origin) else r.origin, np.float32), r.radius
+
+    def sdf_np(x):      # float32 sphere SDF, same op order on both sides
+        return (np.sqrt((x.astype(np.float32) ** 2).sum(-1, dtype=np.float32)) - np.float32(0.5)).astype(np.float32)
+
+    def sdf_t(x):
+        return torch.from_numpy(sdf_np(x.cpu().numpy())).to(x.device)
+
+    train_level, thr = ref_level + 2, 0.02
+    new_ref, o_ref, s_ref, l_ref, tvs_ref, pc_ref = op.octree_update(cfg_scene, ref_tree, ref_origin, ref_scale, ref_level,
+                                                                     train_level, thr, sdf_np, origin_sfm, radius_sfm)
+    data = nrw.octree.octree_update(r, train_level, thr, sdf_fn=sdf_t)
+    assert data["level"] == l_ref and data["voxel_size"] == tvs_ref and data["scale"] == s_ref
+    assert r.fine_octree_data is data and len(pc_ref) > 100
+    tree = {"octree": data["octree"], "prefix": data["spc_data"]["prefix"], "pyramid": data["spc_data"]["pyramid"],
+            "points": data["spc_data"]["points"]}
+    _cmp(tree, new_ref)
+    # and with the real SDF network (nrw_sdf_query): the selection agrees with the restated fp32 network except for
+    # candidates whose SDF is within 1e-4 of the threshold
+    from util_nrw import port
+    P = synth.make_params(seed=0)
+    seen = {}
+
+    def sdf_port(x):
+        with torch.no_grad():
+            v = port.sdf_forward(P, torch.from_numpy(np.ascontiguousarray(x)))[:, 0].numpy()
+        seen["sdf"] = v
+        return v
+
+    op.surface_selection(ref_tree, ref_origin, ref_scale, ref_level, ref_level + 1, np.inf, sdf_port, origin_sfm, radius_sfm)
+    thr2 = float(np.median(seen["sdf"]))
+    pc_ref2, _ = op.surface_selection(ref_tree, ref_origin, ref_scale, ref_level, ref_level + 1, thr2, sdf_port, origin_sfm, radius_sfm)
+    pc_gpu2, _ = nrw.octree.surface_selection(r, ref_level + 1, thr2)
+    near_thr = int((np.abs(seen["sdf"] - thr2) < 1e-4).sum())
+    assert len(pc_ref2) > 100 and abs(pc_gpu2.shape[0] - len(pc_ref2)) <= near_thr
+    data2 = nrw.octree.octree_update(r, ref_level + 1, thr2)
+    assert data2["octree"].numel() > 0 and data2["level"] >= ref_level
