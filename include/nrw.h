@@ -214,6 +214,16 @@ NRW_API int nrw_octree_build(const void* points, int points_are_f64, int n_point
                              int32_t* prefix, int32_t* pyramid, int16_t* points_out, int cap_nonleaf, int cap_total,
                              int32_t* counts_out, void* scratch, void* stream);
 
+/* ---- fused clip + Adam on flat fp32 buffers (train.py:61 gradient_clip_val -> clip_grad_norm_;
+ *      utils/__init__.py:30 torch.optim.Adam(eps=1e-7)) ---------------------------------------------------------- */
+/* acc[0] (device double, zeroed by the caller) += sum g^2; call once per gradient buffer of the clipped group */
+NRW_API int nrw_grad_sumsq(const float* grad, long long n, double* acc, void* stream);
+/* one Adam step (t = step >= 1) on p with moments m, v; the gradient is scaled by min(1, max_norm/(sqrt(*sumsq)+1e-6))
+ * when sumsq != NULL and max_norm > 0 (torch.nn.utils.clip_grad_norm_).  Nothing is read back to the host. */
+NRW_API int nrw_adam_clip_step(float* p, const float* grad, float* m, float* v, long long n, const double* sumsq,
+                               double max_norm, double lr, double beta1, double beta2, double eps, int step,
+                               void* stream);
+
 /* ---- unit-test hooks ---------------------------------------------------------------------- */
 /* D[M,N] = (sum planes of A)[M,K] * (sum planes of B)[N,K]^T from fp32 inputs: splits into planes in
  * scratch (caller-provided, nrw_gemm_test_scratch_bytes) and runs the selected backend. */

@@ -250,6 +250,20 @@ int nrw_octree_build(const void* points, int points_are_f64, int n_points, int l
   NRW_GUARD_END
 }
 
+int nrw_grad_sumsq(const float* grad, long long n, double* acc, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(acc && (n == 0 || grad), NRW_ERR_ARG, "nrw_grad_sumsq: null pointer");
+  return grad_sumsq(grad, n, acc, S(stream));
+  NRW_GUARD_END
+}
+int nrw_adam_clip_step(float* p, const float* grad, float* m, float* v, long long n, const double* sumsq, double max_norm,
+                       double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(n == 0 || (p && grad && m && v), NRW_ERR_ARG, "nrw_adam_clip_step: null pointer");
+  return adam_clip_step(p, grad, m, v, n, sumsq, max_norm, lr, beta1, beta2, eps, step, S(stream));
+  NRW_GUARD_END
+}
+
 long long nrw_gemm_test_scratch_bytes(int M, int N, int K) {
   const long long a = round_up((long long)M * K, 512), b = round_up((long long)N * K, 512);
   return (a + b) * 3 * 2 + 4096;

@@ -17,3 +17,10 @@ long long octree_build_scratch_bytes(int n_points, int level, int cap_nonleaf);
 int octree_build(const void* points, int is_f64, int n, int level, uint8_t* octree, int32_t* prefix, int32_t* pyramid,
                  int16_t* points_out, int cap_nonleaf, int cap_total, int32_t* counts_out, void* scratch, cudaStream_t s);
 }  // namespace nrw
+
+// fused clip + Adam (optim.cu)
+namespace nrw {
+int grad_sumsq(const float* g, long long n, double* acc, cudaStream_t s);
+int adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const double* sumsq, double max_norm, double lr,
+                   double b1, double b2, double eps, int step, cudaStream_t s);
+}  // namespace nrw

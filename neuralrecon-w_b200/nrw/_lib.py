@@ -90,6 +90,9 @@ def lib():
     L.nrw_octree_build_scratch_bytes.restype = ll
     L.nrw_octree_build_scratch_bytes.argtypes = [i32, i32, i32]
     L.nrw_octree_build.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    f64 = C.c_double
+    L.nrw_grad_sumsq.argtypes = [vp, ll, vp, vp]
+    L.nrw_adam_clip_step.argtypes = [vp, vp, vp, vp, ll, vp, f64, f64, f64, f64, f64, i32, vp]
     L.nrw_gemm_test_scratch_bytes.restype = ll
     L.nrw_gemm_test_scratch_bytes.argtypes = [i32, i32, i32]
     L.nrw_gemm_test.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]
@@ -106,7 +109,8 @@ EXPORTS = ["nrw_last_error", "nrw_version", "nrw_param_count", "nrw_param_table"
            "nrw_samples_per_ray", "nrw_upsample_round", "nrw_render_forward", "nrw_render_backward",
            "nrw_composite_forward", "nrw_composite_backward", "nrw_octree_near_far", "nrw_octree_hits",
            "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile",
-           "nrw_gemm_timing", "nrw_ctx_set_backward_planes", "nrw_octree_build_scratch_bytes", "nrw_octree_build"]
+           "nrw_gemm_timing", "nrw_ctx_set_backward_planes", "nrw_octree_build_scratch_bytes", "nrw_octree_build",
+           "nrw_grad_sumsq", "nrw_adam_clip_step"]
 
 
 def check(status, what=""):

@@ -219,6 +219,10 @@ def _io_struct(tensors):
     return io
 
 
+_OUT_KEYS = ("color", "color_sphere", "color_bg", "cdf", "gradients", "weights", "weights_sum", "inside_sphere",
+             "depth", "normals", "gradient_error")
+
+
 class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, rcfg, o, d, z_vals, z_out, sample_dist, a_emb, inv_s, *params):
@@ -235,7 +239,12 @@ class _RenderFn(torch.autograd.Function):
                  sv_z_feed=f(R, T), sv_relax_sum=f(1))
         io = _io_struct(t)
         check(eng.L.nrw_render_forward(eng.ctx, C.byref(rcfg), C.byref(io), stream_ptr()), "nrw_render_forward")
-        ctx.eng, ctx.rcfg, ctx.t = eng, rcfg, t
+        # The returned tensors must NOT sit in ctx.__dict__: output -> grad_fn -> ctx -> output is a cycle through
+        # C++ that Python's gc cannot break (it kept every step's ctx, its tensors and the engine alive).
+        # save_for_backward is the cycle-safe way to keep outputs.
+        ctx.out_keys = _OUT_KEYS
+        ctx.save_for_backward(*[t[k] for k in _OUT_KEYS])
+        ctx.eng, ctx.rcfg, ctx.t = eng, rcfg, {k: v for k, v in t.items() if k not in _OUT_KEYS}
         ctx.inv_s_shape = inv_s.shape
         ctx.n_params = len(params)
         ctx.param_meta = [(p.shape, eng.index[k][1], eng.index[k][2]) for (k, _), p in zip(eng.named_params(), params)]
@@ -246,7 +255,12 @@ class _RenderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, g_cs, g_cb, g_cdf, g_grad, g_w, g_ws, g_inside, g_depth, g_normals, g_ge):
-        eng, rcfg, t = ctx.eng, ctx.rcfg, ctx.t
+        if ctx.t is None:
+            raise NrwError("render backward called twice (retain_graph is not supported: the saved per-sample "
+                           "tensors are released after the first backward)")
+        eng, rcfg = ctx.eng, ctx.rcfg
+        t = dict(ctx.t)
+        t.update(zip(ctx.out_keys, ctx.saved_tensors))
         dev = t["o"].device
         if eng.bound[2] < 1:
             raise NrwError("render was run under no_grad; cannot backpropagate through it")
@@ -265,6 +279,8 @@ class _RenderFn(torch.autograd.Function):
         check(eng.L.nrw_render_backward(eng.ctx, C.byref(rcfg), C.byref(io), C.byref(gr), stream_ptr()),
               "nrw_render_backward")
         eng.last_flat_grad = flat_grad
+        ctx.t = None            # release the per-sample saved tensors now, not when the graph is collected
+        ctx.eng = None
         pgrads = [flat_grad[off:off + numel].view(shape) for shape, off, numel in ctx.param_meta]
         return (None, None, None, None, None, None, None, g_a, g_invs.reshape(ctx.inv_s_shape), *pgrads)
 

@@ -35,13 +35,57 @@ class NeuconWLoss(torch.nn.Module):
         return {k: self.coef * v for k, v in ret.items()}
 
 
+class FusedClipAdam:
+    """clip_grad_norm_(max_norm) + Adam.step (train.py:61 gradient_clip_val; utils/__init__.py:30) on flat fp32
+    buffers through nrw_grad_sumsq / nrw_adam_clip_step: ONE pass over parameter, gradient and moments per buffer, the clip
+    coefficient stays on the device.  Groups are (param_flat, grad_getter) pairs; all groups share one gradient norm,
+    as clip_grad_norm_ over the whole parameter list does."""
+
+    def __init__(self, lr, betas=(0.9, 0.999), eps=1e-7, max_norm=0.99):
+        from . import _lib
+        self._lib, self.L = _lib, _lib.lib()
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self.step_count = 0
+        self.state = {}          # id -> (m, v)
+        self.acc = None
+        self.param_groups = [{"lr": lr}]     # schedulers mutate this, like torch.optim
+
+    def zero_grad(self, set_to_none=True):
+        pass                      # gradients are overwritten by the backward pass
+
+    def step(self, groups):
+        """groups: list of (param tensor, grad tensor), contiguous fp32 on one device."""
+        lib, L = self._lib, self.L
+        groups = [(p, g) for p, g in groups if g is not None]
+        if not groups:
+            return
+        dev = groups[0][0].device
+        if self.acc is None or self.acc.device != dev:
+            self.acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.acc.zero_()
+        self.step_count += 1
+        s = lib.stream_ptr()
+        for p, g in groups:
+            if not (p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32):
+                raise lib.NrwError("FusedClipAdam: parameters and gradients must be contiguous fp32")
+            lib.check(L.nrw_grad_sumsq(lib.ptr(g), g.numel(), lib.ptr(self.acc), s), "nrw_grad_sumsq")
+        lr = self.param_groups[0]["lr"]
+        for p, g in groups:
+            st = self.state.get(p.data_ptr())
+            if st is None:
+                st = self.state[p.data_ptr()] = (torch.zeros_like(p), torch.zeros_like(p))
+            lib.check(L.nrw_adam_clip_step(lib.ptr(p), lib.ptr(g), lib.ptr(st[0]), lib.ptr(st[1]), p.numel(), lib.ptr(self.acc),
+                                           float(self.max_norm), float(lr), float(self.betas[0]), float(self.betas[1]),
+                                           float(self.eps), self.step_count, s), "nrw_adam_clip_step")
+
+
 class TrainSystem:
     """embedding_a + neuconw + nerf + renderer + loss + Adam, i.e. what NeuconWSystem owns."""
 
     def __init__(self, device, n_samples=64, n_importance=64, up_sample_steps=4, n_outside=4, s_val_base=3,
                  n_vocab=5000, n_a=48, origin=(0.0, 0.0, 0.0), radius=1.0, precision=None, chunk_rows=None,
                  batch_size=8192, world_size=1, canonical_lr=1e-4, canonical_bs=4096, anneal_end=50000,
-                 igr_weight=0.0001, mask_weight=0.1, depth_weight=0.1, seed=66):
+                 igr_weight=0.0001, mask_weight=0.1, depth_weight=0.1, seed=66, fused_optimizer=True):
         torch.manual_seed(seed)
         self.device = device
         self.embedding_a = torch.nn.Embedding(n_vocab, n_a).to(device)
@@ -57,7 +101,12 @@ class TrainSystem:
         self.loss = NeuconWLoss(igr_weight=igr_weight, mask_weight=mask_weight, depth_weight=depth_weight)
         self.params = [p for m in (self.embedding_a, self.neuconw, self.nerf) for p in m.parameters()]
         lr = canonical_lr * (world_size * batch_size / canonical_bs)  # train.py:21-25
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, eps=1e-7, weight_decay=0)  # utils/__init__.py:30
+        # utils/__init__.py:30 Adam(eps=1e-7) + train.py:61 gradient_clip_val=0.99
+        self.fused_optimizer = bool(fused_optimizer)
+        if self.fused_optimizer:
+            self.optimizer = FusedClipAdam(lr=lr, eps=1e-7, max_norm=0.99)
+        else:
+            self.optimizer = torch.optim.Adam(self.params, lr=lr, eps=1e-7, weight_decay=0)
         self.anneal_end = anneal_end
         self.global_step = 0
         self.world_size = world_size
@@ -79,7 +128,8 @@ class TrainSystem:
         mark = (lambda n: ev.append((n, _rec()))) if ev is not None else (lambda n: None)
         mark("start")
         self.renderer.nerf_far_override = False
-        self.optimizer.zero_grad(set_to_none=True)
+        for p in self.params:                  # zero_grad(set_to_none=True)
+            p.grad = None
         results = self.forward(rays, ts, label)
         mark("forward")
         loss = sum(self.loss(results, rgbs).values())
@@ -89,7 +139,10 @@ class TrainSystem:
         flat = eng.last_flat_grad
         for k, p in eng.named_params():        # make every .grad a view of the flat gradient buffer
             shape, off, numel = eng.index[k]
-            p.grad = flat[off:off + numel].view(shape)
+            view = flat[off:off + numel].view(shape)
+            if k.endswith("deviation_network.variance") and p.grad is not None:
+                view.copy_(p.grad)             # reaches the parameter through torch glue (inv_s), not through the engine
+            p.grad = view
         if self.world_size > 1:
             dist.all_reduce(flat)                      # one collective for neuconw + nerf (15 MB, NVLink)
             flat.div_(self.world_size)
@@ -97,8 +150,12 @@ class TrainSystem:
             if eg is not None:
                 dist.all_reduce(eg)
                 eg.div_(self.world_size)
-        torch.nn.utils.clip_grad_norm_(self.params, 0.99)
-        self.optimizer.step()
+        if self.fused_optimizer:
+            # the flat buffers hold every neuconw / nerf parameter (the embedding slice of the table is unused there)
+            self.optimizer.step([(eng.flat, flat), (self.embedding_a.weight.data, self.embedding_a.weight.grad)])
+        else:
+            torch.nn.utils.clip_grad_norm_(self.params, 0.99)
+            self.optimizer.step()
         mark("optimizer")
         self.global_step += 1
         return loss.detach()
