@@ -163,12 +163,16 @@ __global__ void boundary_kernel(int R, int S0, int nb, const float* __restrict__
   const int n_near = nb / 2, n_far = nb - n_near;
   const float* zr = z + (long long)r * S0;
   float* o = out + (long long)r * (S0 + nb);
-  // candidate runs (each ascending when near <= z0 and zlast <= far)
+  // The reference sorts the concatenation (torch.sort, renderer.py:565).  Each run is monotone, so a 3-way merge gives
+  // the same values: the near run ascends when near <= z0 and DESCENDS when the fine sampling window starts before the
+  // (octree-overridden) near, the far run likewise; descending runs are walked from their last element.
   int a = 0, b = 0, c = 0;
   const float z0 = zr[0], zl = zr[S0 - 1], nr = near[r], fr = far[r];
+  const bool a_desc = z0 < nr, b_desc = fr < zl;
   for (int k = 0; k < S0 + nb; ++k) {
-    const float va = a < n_near ? NRW_ADD(nr, NRW_MUL(NRW_SUB(z0, nr), nrw_linspace_f32(0.0f, 1.0f, n_near + 1, a))) : INFINITY;
-    const float vb = b < n_far ? NRW_ADD(zl, NRW_MUL(NRW_SUB(fr, zl), nrw_linspace_f32(0.0f, 1.0f, n_far + 1, b + 1))) : INFINITY;
+    const int ia = a_desc ? n_near - 1 - a : a, ib = b_desc ? n_far - 1 - b : b;
+    const float va = a < n_near ? NRW_ADD(nr, NRW_MUL(NRW_SUB(z0, nr), nrw_linspace_f32(0.0f, 1.0f, n_near + 1, ia))) : INFINITY;
+    const float vb = b < n_far ? NRW_ADD(zl, NRW_MUL(NRW_SUB(fr, zl), nrw_linspace_f32(0.0f, 1.0f, n_far + 1, ib + 1))) : INFINITY;
     const float vc = c < S0 ? zr[c] : INFINITY;
     // smallest first; ties resolved in concatenation order [near run, far run, z]
     if (a < n_near && va <= vb && va <= vc) { o[k] = va; ++a; }
