@@ -123,3 +123,28 @@ void nrw_ref_coarse(int R, int n_samples, int n_outside, int perturb, const floa
     }
   }
 }
+
+/* Boundary samples of the fine-sampling branch (rendering/renderer.py:546-566): bound_near_num = nb/2 values
+ * near + (z_0 - near) * linspace(0,1,n_near+1)[:-1], bound_far_num = nb - nb/2 values
+ * z_last + (far - z_last) * linspace(0,1,n_far+1)[1:], concatenated with z and sorted (torch.sort).  Each run is
+ * monotone (DESCENDING when the sampling window starts before near / ends after far), so the sort is restated as a
+ * 3-way merge that walks descending runs from their end; the sorted VALUES are what the reference produces. */
+void nrw_ref_boundary(int R, int S0, int nb, const float* near, const float* far, const float* z_all, float* out_all) {
+  const int n_near = nb / 2, n_far = nb - n_near;
+  for (int r = 0; r < R; ++r) {
+    const float* zr = z_all + (long)r * S0;
+    float* o = out_all + (long)r * (S0 + nb);
+    const float z0 = zr[0], zl = zr[S0 - 1], nr = near[r], fr = far[r];
+    const int a_desc = z0 < nr, b_desc = fr < zl;
+    int a = 0, b = 0, c = 0;
+    for (int k = 0; k < S0 + nb; ++k) {
+      const int ia = a_desc ? n_near - 1 - a : a, ib = b_desc ? n_far - 1 - b : b;
+      const float va = a < n_near ? NRW_ADD(nr, NRW_MUL(NRW_SUB(z0, nr), nrw_linspace_f32(0.0f, 1.0f, n_near + 1, ia))) : INFINITY;
+      const float vb = b < n_far ? NRW_ADD(zl, NRW_MUL(NRW_SUB(fr, zl), nrw_linspace_f32(0.0f, 1.0f, n_far + 1, ib + 1))) : INFINITY;
+      const float vc = c < S0 ? zr[c] : INFINITY;
+      if (a < n_near && va <= vb && va <= vc) { o[k] = va; ++a; }
+      else if (b < n_far && vb <= vc) { o[k] = vb; ++b; }
+      else { o[k] = vc; ++c; }
+    }
+  }
+}

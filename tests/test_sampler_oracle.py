@@ -50,3 +50,25 @@ def test_c_sampler_edge_cases():
     assert sorted(order[0].tolist()) == list(range(m + 1))
     z_new4, _, inds4, _, _ = oc.upsample_round(o, d, z, sdf, 4, 64.0)
     assert np.all(inds4 >= 1) and np.all(inds4 <= m - 1 + 1)
+
+
+def test_boundary_samples_match_torch_sort():
+    """renderer.py:546-566 incl. the fine-sampling case where the window starts before near / ends after far."""
+    import torch
+    rng = np.random.RandomState(0)
+    R, S0, nb = 64, 24, 10
+    z = np.sort(rng.uniform(2.0, 4.0, (R, S0)).astype(np.float32), axis=1)
+    near = z[:, 0] - rng.uniform(-0.3, 0.3, R).astype(np.float32)        # both signs: ascending and descending near runs
+    far = z[:, -1] + rng.uniform(-0.3, 0.3, R).astype(np.float32)
+    near[:4] = z[:4, 0]                                                   # degenerate: near == z_0
+    far[:4] = z[:4, -1]
+    got = oc.boundary(near, far, z, nb)
+    zt, nt, ft = torch.from_numpy(z), torch.from_numpy(near)[:, None], torch.from_numpy(far)[:, None]
+    n_near = nb // 2
+    n_far = nb - n_near
+    bn = nt + (zt[:, 0][:, None] - nt) * torch.linspace(0.0, 1.0, n_near + 1)[:-1][None, :]
+    bf = zt[:, -1][:, None] + (ft - zt[:, -1][:, None]) * torch.linspace(0.0, 1.0, n_far + 1)[1:][None, :]
+    want, _ = torch.sort(torch.cat([bn, bf, zt], dim=-1), dim=-1)
+    assert got.shape == tuple(want.shape)
+    assert np.all(got[:, 1:] >= got[:, :-1])
+    assert np.abs(got - want.numpy()).max() <= 4e-7                      # torch.linspace vs the written-down linspace: 1 ulp

@@ -13,8 +13,8 @@ def lib():
     global _lib
     if _lib is None:
         so = os.path.join(ROOT, "oracle", "_build", "libsampler_ref.so")
-        if not os.path.isfile(so):
-            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
+        # always ask make: a no-op when oracle/_build is newer than the sources, a rebuild after an edit
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
         _lib = C.CDLL(so)
     return _lib
 
@@ -47,3 +47,12 @@ def coarse(n_samples, n_outside, near, far, s_near=None, s_far=None, u_ray=None,
     lib().nrw_ref_coarse(C.c_int(R), C.c_int(n_samples), C.c_int(n_outside), C.c_int(int(u_ray is not None)), _p(near), _p(far),
                          _p(s_near), _p(s_far), _p(u_ray), _p(u_out), _p(z), _p(zo), _p(sd))
     return z, zo[:, :n_outside], sd
+
+
+def boundary(near, far, z, nb):
+    """renderer.py:546-566 -> sorted [R, S0+nb]"""
+    R, S0 = z.shape
+    near, far, z = (np.ascontiguousarray(x, np.float32) for x in (near, far, z))
+    out = np.zeros((R, S0 + nb), np.float32)
+    lib().nrw_ref_boundary(C.c_int(R), C.c_int(S0), C.c_int(nb), _p(near), _p(far), _p(z), _p(out))
+    return out
