@@ -114,6 +114,11 @@ NRW_API int nrw_upsample_round(int R, int m, int n_new, float inv_s, const float
                                float* z_merged /*[R,m+n_new]*/, int32_t* inds /*[R,n_new]*/,
                                int32_t* order /*[R,m+n_new]*/, void* stream);
 
+/* boundary samples of the fine-sampling branch (stage-wise bit-exactness test; renderer.py:546-566):
+ * z [R,S0] ascending -> out [R,S0+nb] = sort(cat(nb/2 samples on [near,z_0), nb-nb/2 on (z_last,far], z)) */
+NRW_API int nrw_boundary_samples(int R, int S0, int nb, const float* near, const float* far, const float* z,
+                                 float* out, void* stream);
+
 /* ---- NeuconWRenderer.render core (rendering/renderer.py:157-228,570-783) ----------------- */
 typedef struct {
   int R, S, n_outside;        /* T = S + n_outside */

@@ -182,6 +182,16 @@ int nrw_upsample_round(int R, int m, int n_new, float inv_s, const float* o, con
   NRW_GUARD_END
 }
 
+int nrw_boundary_samples(int R, int S0, int nb, const float* near, const float* far, const float* z, float* out,
+                         void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(S0 >= 1 && nb >= 0, NRW_ERR_ARG, "boundary_samples: S0=%d nb=%d", S0, nb);
+  if (R == 0) return NRW_OK;
+  NRW_CHECK(near && far && z && out, NRW_ERR_ARG, "boundary_samples: null pointer");
+  return launch_boundary(R, S0, nb, near, far, z, out, S(stream));
+  NRW_GUARD_END
+}
+
 int nrw_render_forward(nrw_ctx* ctx, const nrw_render_cfg* cfg, const nrw_render_io* io, void* stream) {
   NRW_GUARD_BEGIN
   NRW_CHECK(ctx && cfg && io, NRW_ERR_ARG, "render_forward: null argument");

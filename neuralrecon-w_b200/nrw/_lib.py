@@ -81,6 +81,7 @@ def lib():
     L.nrw_sample.argtypes = [vp, C.POINTER(SamplerCfg), i32] + [vp] * 14
     L.nrw_samples_per_ray.argtypes = [C.POINTER(SamplerCfg), i32]
     L.nrw_upsample_round.argtypes = [i32, i32, i32, f32] + [vp] * 10
+    L.nrw_boundary_samples.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     L.nrw_render_forward.argtypes = [vp, C.POINTER(RenderCfg), C.POINTER(RenderIO), vp]
     L.nrw_render_backward.argtypes = [vp, C.POINTER(RenderCfg), C.POINTER(RenderIO), C.POINTER(RenderGrads), vp]
     L.nrw_composite_forward.argtypes = [C.POINTER(RenderCfg), C.POINTER(RenderIO)] + [vp] * 7
@@ -110,7 +111,7 @@ EXPORTS = ["nrw_last_error", "nrw_version", "nrw_param_count", "nrw_param_table"
            "nrw_composite_forward", "nrw_composite_backward", "nrw_octree_near_far", "nrw_octree_hits",
            "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile",
            "nrw_gemm_timing", "nrw_ctx_set_backward_planes", "nrw_octree_build_scratch_bytes", "nrw_octree_build",
-           "nrw_grad_sumsq", "nrw_adam_clip_step"]
+           "nrw_grad_sumsq", "nrw_adam_clip_step", "nrw_boundary_samples"]
 
 
 def check(status, what=""):

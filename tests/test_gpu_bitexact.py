@@ -147,3 +147,25 @@ def test_octree_no_intersections():
     d = np.tile(np.array([[0, 1.0, 0]], np.float32), (16, 1))
     gn, gf, gpid, gcnt, *_ = _trace_cuda(tree, 4, ro, d, np.zeros(3, np.float32), 1.0)
     assert (gcnt == 0).all() and (gpid == -1).all() and (gn == 0).all() and (gf == 0).all()
+
+
+def test_boundary_samples_bitexact():
+    """renderer.py:546-566: the CUDA merge of the boundary samples equals the written-down C restatement bit for bit,
+    for ascending AND descending boundary runs (fine-sampling window starting before near / ending after far)."""
+    from nrw import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(2)
+    R, S0, nb = 257, 40, 10
+    z = np.sort(rng.uniform(2.0, 4.0, (R, S0)).astype(np.float32), axis=1)
+    near = (z[:, 0] - rng.uniform(-0.3, 0.3, R)).astype(np.float32)
+    far = (z[:, -1] + rng.uniform(-0.3, 0.3, R)).astype(np.float32)
+    near[:5], far[:5] = z[:5, 0], z[:5, -1]
+    want = oc.boundary(near, far, z, nb)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    n_, f_, z_ = t(near), t(far), t(z)
+    out = torch.zeros(R, S0 + nb, device="cuda")
+    _lib.check(L.nrw_boundary_samples(R, S0, nb, _lib.ptr(n_), _lib.ptr(f_), _lib.ptr(z_), _lib.ptr(out), _lib.stream_ptr()),
+               "nrw_boundary_samples")
+    got = out.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.all(got[:, 1:] >= got[:, :-1])
