@@ -85,3 +85,27 @@ def test_render_refuses_cpu_tensors():
     b = synth.make_rays(4, cfg)
     with pytest.raises(nrw.NrwError):
         s["renderer"].render(b["rays"], b["ts"], b["label"])
+
+
+def test_octree_and_optimizer_entry_points_fail_loudly_without_cuda():
+    """K0 / refresh / fused optimiser have no CPU path either: clear errors, no silent fallback."""
+    import nrw
+    import nrw.octree as noct
+    from util_nrw import build_system
+
+    with pytest.raises(nrw.NrwError):
+        noct.build_octree(torch.zeros(8, 3, dtype=torch.float64), 4)          # CPU tensor
+    cfg = synth.PathConfig(n_samples=8, n_importance=8, up_sample_steps=2)
+    r = build_system(synth.make_params(0), cfg, device="cpu")["renderer"]
+    with pytest.raises(nrw.NrwError):
+        r.get_octree("cpu")                                                   # no sfm_points / scene_config given
+    with pytest.raises(nrw.NrwError):
+        noct.octree_update(r, 5, 0.01)                                        # no scene_config
+    # argument validation of the C entry points happens before any CUDA call
+    from nrw import _lib
+    L = _lib.lib()
+    assert L.nrw_octree_build(None, 0, 4, 20, None, None, None, None, 1, 1, None, None, None) != 0
+    assert b"octree_build" in L.nrw_last_error()
+    assert L.nrw_adam_clip_step(None, None, None, None, 5, None, 0.99, 1e-4, 0.9, 0.999, 1e-7, 1, None) != 0
+    assert L.nrw_boundary_samples(4, 0, 2, None, None, None, None, None) != 0
+    assert L.nrw_octree_build_scratch_bytes(1000, 6, 6000) > 0
