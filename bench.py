@@ -126,50 +126,82 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference(workload, n_rays_cpu, steps, warmup, threads):
-    """The reference's own PyTorch CPU path, restated in oracle/neuconw_port.py (pinned to the unmodified
-    reference by tests/golden), timed on the host cores: render + loss + backward on a bounded ray sample."""
+def _ref_cfg(workload):
+    from oracle import synth
+
+    w = WORKLOADS[workload]
+    return synth.PathConfig(n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=w["up_sample_steps"],
+                            n_outside=w["n_outside"], perturb=1.0)
+
+
+def reference_kind():
+    """"reference": the UNMODIFIED reference (oracle/_ref = verbatim copy made by oracle/fetch_ref.py, or /root/reference);
+    "port": the pinned restatement oracle/neuconw_port.py (only when no reference copy travelled to this box)."""
+    from oracle import ref_runner
+
+    return "reference" if ref_runner.available() else "port"
+
+
+def make_reference_stepper(workload, device):
+    """Returns (kind, step(batch)) running one full training step of the reference on `device`:
+    zero_grad -> NeuconWRenderer.render -> NeuconWLoss -> backward -> clip_grad_norm_(0.99) -> Adam(eps=1e-7)."""
+    from oracle import synth
+
+    cfg = _ref_cfg(workload)
+    if reference_kind() == "reference":
+        from oracle import ref_runner
+
+        r = ref_runner.RefRunner(cfg, synth.make_params(seed=0), device=device)
+        return "reference", cfg, (lambda b: r.train_step(b, perturb_overwrite=-1))
     from oracle import neuconw_port as port
+
+    P = {k: v.to(device) for k, v in synth.make_params(seed=0).items()}
+    return "port", cfg, (lambda b: port.train_step(P, cfg, b, perturb_overwrite=-1)[1])
+
+
+def cpu_reference(workload, n_rays_cpu, steps, warmup, threads):
+    """The reference's own PyTorch CPU path timed on the host cores: one full training step per sample batch."""
     from oracle import synth
 
     torch.set_num_threads(threads)
-    w = WORKLOADS[workload]
-    cfg = synth.PathConfig(n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=w["up_sample_steps"],
-                           n_outside=w["n_outside"], perturb=1.0)
-    P = synth.make_params(seed=0)
+    kind, cfg, step = make_reference_stepper(workload, "cpu")
     batch = synth.make_rays(n_rays_cpu, cfg, seed=1)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        port.train_step(P, cfg, batch, perturb_overwrite=-1)
+        step(batch)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return n_rays_cpu / dt, dt
+    return n_rays_cpu / dt, dt, kind
 
 
-def torch_gpu_reference(workload, n_rays, steps, device):
-    """Same restated reference ops on CUDA tensors (= what the reference executes on a GPU: stock
-    torch.nn / cuBLAS fp32), on a bounded ray sample; the '>= 4x' denominator of BASELINE.json."""
-    from oracle import neuconw_port as port
+def torch_gpu_reference(workload, n_rays, steps, warmup, device):
+    """The reference's stock torch.nn / cuBLAS fp32 path on THIS GPU (the '>= 4x' denominator of BASELINE.json),
+    at the full batch of the workload when it fits in HBM (halved on OOM until it does)."""
     from oracle import synth
 
-    w = WORKLOADS[workload]
-    cfg = synth.PathConfig(n_samples=w["n_samples"], n_importance=w["n_importance"], up_sample_steps=w["up_sample_steps"],
-                           n_outside=w["n_outside"], perturb=1.0)
-    P = {k: v.to(device) for k, v in synth.make_params(seed=0).items()}
-    batch = {k: v.to(device) for k, v in synth.make_rays(n_rays, cfg, seed=1).items()}
+    kind, cfg, step = make_reference_stepper(workload, device)
+    while True:
+        try:
+            batch = {k: v.to(device) for k, v in synth.make_rays(n_rays, cfg, seed=1).items()}
+            for _ in range(warmup):
+                step(batch)
+            torch.cuda.synchronize()
+            break
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            n_rays //= 2
+            if n_rays < 64:
+                raise
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for _ in range(2):
-        port.train_step(P, cfg, batch, perturb_overwrite=-1)
-    torch.cuda.synchronize()
     ev[0].record()
     for _ in range(steps):
-        port.train_step(P, cfg, batch, perturb_overwrite=-1)
+        step(batch)
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / steps
-    return n_rays / (ms * 1e-3), ms
+    return n_rays / (ms * 1e-3), ms, n_rays, kind
 
 
 def main():
@@ -182,7 +214,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--chunk_rows", type=int, default=int(os.environ.get("NRW_CHUNK_ROWS", 262144)))
-    ap.add_argument("--cpu_rays", type=int, default=128)
+    ap.add_argument("--cpu_rays", type=int, default=512)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_torch_gpu_ref", action="store_true")
     ap.add_argument("--no_other_modes", action="store_true")
@@ -204,13 +236,15 @@ def main():
         if rank != 0:
             return
         threads = min(os.cpu_count() or 1, 64)   # beyond ~64 threads MKL on these layer sizes slows down
-        rps, dt = cpu_reference(args.workload, args.cpu_rays, max(1, min(args.steps, 3)), 1 if args.warmup else 0, threads)
+        rps, dt, kind = cpu_reference(args.workload, args.cpu_rays, max(1, args.steps), max(0, args.warmup), threads)
+        src = {"reference": "UNMODIFIED reference NeuconWRenderer.render + NeuconWLoss + backward + clip + Adam (oracle/_ref, torch CPU fp32)",
+               "port": "oracle/neuconw_port.py restatement (no reference copy on this box), torch CPU fp32"}[kind]
         line = {"impl": "reference", "metric": "training rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
-                "steps": max(1, min(args.steps, 3)), "warmup": 1 if args.warmup else 0, "ms_per_step": dt * 1e3,
+                "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                                 "sample": f"{args.cpu_rays} rays x {S} samples per step (render+loss+backward, torch CPU fp32, oracle/neuconw_port.py)"},
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind,
+                                 "sample": f"{args.cpu_rays} of the {w['rays']} rays x {S} samples per step; {src}"},
                 "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -353,16 +387,25 @@ def main():
                 import gc
                 gc.collect()
                 torch.cuda.empty_cache()
-                rps, rms = torch_gpu_reference(args.workload, 1024, 3, device)
-                line["reference_torch_gpu"] = {"value": rps, "unit": "rays/s", "ms_per_step": rms,
-                                               "sample": f"1024 rays x {S} samples, stock torch fp32 ops of the reference path on this GPU"}
+                rps, rms, n_ref, kind = torch_gpu_reference(args.workload, R, 20, 5, device)
+                gref = {"value": rps, "unit": "rays/s", "ms_per_step": rms, "kind": kind, "rays": n_ref, "steps": 20, "warmup": 5,
+                        "speedup_of_this_arm": line["value"] / rps, "e2e_speedup_of_this_arm": line["e2e"]["value"] / rps,
+                        "sample": f"{n_ref} rays x {S} samples per step, full training step of the "
+                                  f"{'UNMODIFIED reference (oracle/_ref)' if kind == 'reference' else 'restated port'} on this GPU (stock torch fp32 / cuBLAS)"}
+                line["reference_torch_gpu"] = gref
+                line["roofline"]["reference_torch_gpu"] = gref       # kept by the driver with the roofline object
             except Exception as e:  # noqa
                 line["reference_torch_gpu"] = {"error": str(e)[:200]}
+            gc.collect()
+            torch.cuda.empty_cache()
         if not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 64)   # beyond ~64 threads MKL on these layer sizes slows down
-            rps, dt = cpu_reference(args.workload, args.cpu_rays, 2, 1, threads)
-            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_rays} rays x {S} samples per step, 2 timed steps (render+loss+backward, torch CPU fp32)"}
+            rps, dt, kind = cpu_reference(args.workload, args.cpu_rays, 2, 1, threads)
+            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind,
+                                    "sample": f"{args.cpu_rays} of the {R} rays x {S} samples per step, 1 warm-up + 2 timed full training steps "
+                                              f"({'UNMODIFIED reference, oracle/_ref' if kind == 'reference' else 'restated port'}, torch CPU fp32)"}
+            if "reference_torch_gpu" in line and "value" in line["reference_torch_gpu"]:
+                line["cpu_baseline"]["gpu_reference"] = line["reference_torch_gpu"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,19 +1,32 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference modules from /root/reference (build container) or from the verbatim copy
+``oracle/_ref`` made by ``oracle/fetch_ref.py`` (git-ignored; travels to the GPU box).
 
 TEST INFRASTRUCTURE.  The reference imports ~10 third-party packages at module
 scope that are absent here (open3d, kaolin, pytorch_lightning, ...).  None of
 them is touched on the cached-near/far training path, so they
 are replaced by inert stand-ins in ``sys.modules`` before the import.
 
-``/root/reference`` does not exist on the GPU box: callers must check
-``available()`` first; nothing under ``-m gpu`` may depend on this module.
+``/root/reference`` does not exist on the GPU box; there ``oracle/_ref`` (sha256-verified against its
+manifest) is used.  Callers must check ``available()`` first.
 """
 import os
 import sys
 import types
 from unittest import mock
 
-REF_ROOT = os.environ.get("NRW_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve_root():
+    env = os.environ.get("NRW_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/rendering/renderer.py"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REF_ROOT = _resolve_root()
 
 _STUBS = [
     "open3d", "kaolin", "kaolin.ops", "kaolin.ops.spc", "kaolin.render",
