@@ -124,7 +124,8 @@ typedef struct {
   int R, S, n_outside;        /* T = S + n_outside */
   float cos_anneal_ratio;
   const float* background_rgb; /* device [3] or NULL (renderer.py:753-754) */
-  int reserved0;
+  int reserved0;               /* generation stamp: render_backward reuses the cached forward activations only when
+                                  it equals the stamp of the render_forward call that produced them (else recompute) */
   int trim_sphere;
 } nrw_render_cfg;
 

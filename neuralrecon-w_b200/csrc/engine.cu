@@ -505,7 +505,7 @@ int render_forward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& i
   NRW_TRY(composite_forward(cfg, io, io.sv_sdf, io.gradients, io.sv_rgb, bg ? io.sv_bg_alpha : nullptr,
                             bg ? io.sv_bg_rgb : nullptr, c.ge_acc, s));
   c.fwd_cached = cache;
-  c.cached_R = R; c.cached_S = S; c.cached_T = T;
+  c.cached_R = R; c.cached_S = S; c.cached_T = T; c.cached_gen = cfg.reserved0;
   return NRW_OK;
 }
 
@@ -521,7 +521,8 @@ int render_backward(nrw_ctx& c, const nrw_render_cfg& cfg, const nrw_render_io& 
                              bg ? io.sv_bg_rgb : nullptr, c.g_dsdf, c.g_dnrm, c.g_drgb, bg ? c.g_dbga : nullptr,
                              bg ? c.g_dbgc : nullptr, g.grad_inv_s, s));
   // forward activations still resident in per-chunk slots?  otherwise recompute chunk by chunk into slot 0
-  const bool cached = c.fwd_cached && c.cached_R == R && c.cached_S == S && c.cached_T == T;
+  // (the generation stamp guards against a second render_forward having overwritten the slots: ADVICE r1)
+  const bool cached = c.fwd_cached && c.cached_R == R && c.cached_S == S && c.cached_T == T && c.cached_gen == cfg.reserved0;
   if (bg) {
     const int rc = c.Mc / T;
     for (int r0 = 0, ci = 0; r0 < R; r0 += rc, ++ci) {

@@ -30,7 +30,7 @@ struct nrw_ctx {
   std::vector<FwdNerfSlot> nerf_slots;
   int n_slots_sdf = 1, n_slots_nerf = 1;
   bool fwd_cached = false;          // slots hold the forward of the last render_forward call
-  int cached_R = 0, cached_S = 0, cached_T = 0;
+  int cached_R = 0, cached_S = 0, cached_T = 0, cached_gen = 0;   // gen: nrw_render_cfg::reserved0 of that call
   void use_sdf_slot(int i) {
     const FwdSdfSlot& s = sdf_slots[i];
     PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm;

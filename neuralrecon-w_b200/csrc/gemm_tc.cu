@@ -725,12 +725,21 @@ void gemm_tc_set_profile_buffer(unsigned long long* p) { g_prof_ptr = p; }
 static long long g_tc_launches = 0;
 long long gemm_tc_launch_count() { return g_tc_launches; }
 
+// per-device state (cudaFuncSetAttribute and the SM count are per device; a process may touch several GPUs)
+static constexpr int MAX_DEV = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEV) ? dev : 0;
+}
+
 template <int BN, int MN>
 static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEV] = {false};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int items = p.m_tiles * p.n_tiles * p.k_slices;
   const int grid = items < n_sm ? items : n_sm;
@@ -800,12 +809,10 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   NRW_CHECK(g.M > 0 && g.N > 0 && g.K > 0, NRW_ERR_ARG, "gemm_tc: empty problem %d %d %d", g.M, g.N, g.K);
   NRW_CHECK(g.n_planes >= 1 && g.n_planes <= 3, NRW_ERR_ARG, "gemm_tc: n_planes=%d", g.n_planes);
   NRW_CHECK(g.k_slices == 1 || g.epi.atomic, NRW_ERR_ARG, "gemm_tc: split-K needs an atomic epilogue");
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    NRW_CUDA_OK(cudaGetDevice(&dev));
-    NRW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static int n_sm_dev[MAX_DEV] = {0};
+  const int dev = current_device();
+  if (!n_sm_dev[dev]) NRW_CUDA_OK(cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int n_sm = n_sm_dev[dev];
   int BN;
   static const int bn_pref = getenv("NRW_TC_BN") ? atoi(getenv("NRW_TC_BN")) : 0;   // tuning override
   if (g.N <= 64) BN = 64;
@@ -834,11 +841,11 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.N, g.K, g.B.ld, 64, BK));
       }
     }
-    static bool attr2[2] = {false, false};
-    if (!attr2[g.mn_major ? 1 : 0]) {
+    static bool attr2[MAX_DEV][2] = {{false, false}};
+    if (!attr2[dev][g.mn_major ? 1 : 0]) {
       if (g.mn_major) NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       else NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr2[g.mn_major ? 1 : 0] = true;
+      attr2[dev][g.mn_major ? 1 : 0] = true;
     }
     const int items = p.m_tiles * p.n_tiles * p.k_slices;
     int pairs = n_sm / 2;

@@ -90,23 +90,32 @@ class Engine:
             view.copy_(p.data.to(device=device, dtype=torch.float32))
             p.data = view
         self.flat = flat
+        self.packed_version = None
         return named
 
     # ---- context / workspace ----------------------------------------------------------------
-    def ensure(self, device, max_rays, max_T, with_backward, S=None):
+    def ensure(self, device, max_rays, max_T, with_backward, S=None, chunk_hint=0):
         """(Re)bind the workspace.  With backward enabled, as many chunk slots as the memory budget
         (NRW_SLOT_BUDGET_GB, default 60 % of free HBM) allows keep their forward activations resident so
-        the backward pass does not recompute the forward (the 180 GB of a B200 hold a full 8192x128 batch)."""
+        the backward pass does not recompute the forward (the 180 GB of a B200 hold a full 8192x128 batch).
+
+        Bounds only ever grow.  `max_rays x max_T` sizes the PER-RAY scratch of render / sample; point queries
+        (sdf, neuconw_forward, nerf_forward) need chunk buffers only and pass `chunk_hint` (rows they would like one
+        chunk to hold) instead of inflating the ray bound, so a 1M-point SDF query after a training step neither
+        allocates per-ray scratch for 1M rays nor costs the training path its forward slots."""
         b = self.bound
+        want_chunk = min(self.chunk_rows, ((max(int(chunk_hint), 0) + 127) // 128) * 128)
         if (self.workspace is not None and self.workspace.device == device and b[0] >= int(max_rays) and b[1] >= int(max_T)
-                and b[2] >= int(with_backward)):
+                and b[2] >= int(with_backward) and b[3] >= want_chunk):
             return
         max_rays = max(int(max_rays), 1, b[0])
         max_T = max(int(max_T), 2, b[1])
         with_backward = max(int(with_backward), b[2])
+        if S:
+            self.bound_S = max(int(S), getattr(self, "bound_S", 0))
         # chunk: as large as configured, but never (much) larger than the whole problem
         need_rows = ((max_rays * max_T + 127) // 128) * 128
-        chunk = max(min(self.chunk_rows, max(need_rows, 4096)), ((max_T + 127) // 128) * 128)
+        chunk = max(min(self.chunk_rows, max(need_rows, 4096, want_chunk)), ((max_T + 127) // 128) * 128, b[3])
         with torch.cuda.device(device):
             if self.packed is None or self.packed.device != device:
                 nb = self.L.nrw_packed_bytes(self.ctx)
@@ -115,7 +124,7 @@ class Engine:
             torch.cuda.empty_cache()
             ns_sdf = ns_nerf = 1
             if with_backward and os.environ.get("NRW_RECOMPUTE", "0") != "1":
-                S_eff = int(S) if S else max_T
+                S_eff = getattr(self, "bound_S", 0) or max_T
                 want_sdf = -(-max_rays // max(chunk // S_eff, 1))
                 want_nerf = -(-max_rays // max(chunk // max_T, 1))
                 free, _total = torch.cuda.mem_get_info(device)
@@ -133,10 +142,17 @@ class Engine:
                   "nrw_ctx_bind")
         self.bound = (max_rays, max_T, with_backward, chunk)
         self.slots = (ns_sdf, ns_nerf)
+        self.packed_version = None        # the packed area may have moved / been re-created
 
     def pack(self, device):
+        """Weight-norm materialisation + plane split of every layer (nrw_pack_weights), ONCE per parameter version:
+        torch bumps the version counter of the flat buffer on every in-place update of a view (optimizer.step,
+        load_state_dict, .copy_), FusedClipAdam bumps it explicitly after writing through the raw pointer."""
         named = self.flatten(device)
-        check(self.L.nrw_pack_weights(self.ctx, ptr(self.flat), stream_ptr()), "nrw_pack_weights")
+        token = (self.flat.data_ptr(), self.flat._version)
+        if getattr(self, "packed_version", None) != token:
+            check(self.L.nrw_pack_weights(self.ctx, ptr(self.flat), stream_ptr()), "nrw_pack_weights")
+            self.packed_version = token
         return named
 
     # ---- operations -------------------------------------------------------------------------
@@ -144,7 +160,7 @@ class Engine:
         """SDF values for pts [n,3] -> [n] (NeuconWRenderer.sdf, rendering/renderer.py:947-949)."""
         pts = pts.detach().reshape(-1, 3).contiguous().float()
         n, dev = pts.shape[0], pts.device
-        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
+        self.ensure(dev, 1, 2, 0, chunk_hint=n)
         self.pack(dev)
         out = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
         check(self.L.nrw_sdf_query(self.ctx, ptr(pts), pts.shape[0], ptr(out), stream_ptr()), "nrw_sdf_query")
@@ -153,7 +169,7 @@ class Engine:
     def neuconw_forward(self, pts, dirs, a, want_rgb=True):
         pts = pts.detach().reshape(-1, 3).contiguous().float()
         n, dev = pts.shape[0], pts.device
-        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
+        self.ensure(dev, 1, 2, 0, chunk_hint=n)
         self.pack(dev)
         sdf = torch.empty(n, dtype=torch.float32, device=dev)
         nrm = torch.empty(n, 3, dtype=torch.float32, device=dev)
@@ -167,7 +183,7 @@ class Engine:
     def nerf_forward(self, pts4, dirs, a):
         pts4 = pts4.detach().reshape(-1, 4).contiguous().float()
         n, dev = pts4.shape[0], pts4.device
-        self.ensure(dev, max(1, min(n, 1 << 21) // 2), 2, 0)
+        self.ensure(dev, 1, 2, 0, chunk_hint=n)
         self.pack(dev)
         dens = torch.empty(n, 1, dtype=torch.float32, device=dev)
         rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
@@ -238,6 +254,10 @@ class _RenderFn(torch.autograd.Function):
                  gradient_error=f(1), sv_sdf=f(R, S), sv_rgb=f(R, S, 3), sv_bg_alpha=f(R, T), sv_bg_rgb=f(R, T, 3),
                  sv_z_feed=f(R, T), sv_relax_sum=f(1))
         io = _io_struct(t)
+        # generation stamp: the forward activations live in the context's shared slots; render_backward only trusts them
+        # when the stamp matches (two grad-enabled renders followed by backward of the first -> recompute path)
+        eng.generation = getattr(eng, "generation", 0) + 1
+        rcfg.reserved0 = eng.generation
         check(eng.L.nrw_render_forward(eng.ctx, C.byref(rcfg), C.byref(io), stream_ptr()), "nrw_render_forward")
         # The returned tensors must NOT sit in ctx.__dict__: output -> grad_fn -> ctx -> output is a cycle through
         # C++ that Python's gc cannot break (it kept every step's ctx, its tensors and the engine alive).

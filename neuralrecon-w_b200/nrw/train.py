@@ -77,6 +77,7 @@ class FusedClipAdam:
             lib.check(L.nrw_adam_clip_step(lib.ptr(p), lib.ptr(g), lib.ptr(st[0]), lib.ptr(st[1]), p.numel(), lib.ptr(self.acc),
                                            float(self.max_norm), float(lr), float(self.betas[0]), float(self.betas[1]),
                                            float(self.eps), self.step_count, s), "nrw_adam_clip_step")
+            torch._C._increment_version([p])       # written through the raw pointer: tell torch (and Engine.pack) it changed
 
 
 class TrainSystem:
@@ -120,21 +121,32 @@ class TrainSystem:
         return self.renderer.render(rays, ts, label, background_rgb=torch.zeros([1, 3], device=rays.device),
                                     cos_anneal_ratio=self.cos_anneal_ratio())
 
-    def training_step(self, batch):
-        """training_step + backward + DDP-mean all-reduce + clip(0.99) + Adam (neuconw_system.py:337-360,
-        train.py:61).  Returns the detached loss tensor (device)."""
+    def filter_rays(self, batch):
+        """RAY_MASK_LIST black list of training_step (neuconw_system.py:345-355): rays whose semantic label is person /
+        car / bicycle / minibike are dropped before rendering.  Batches drawn from nrw.raycache.RayCache arrive already
+        filtered and compacted on the device (key "n_valid"); anything else is filtered here with the reference's
+        boolean indexing (one device->host sync for the count, as in the reference)."""
+        if "n_valid" in batch or not self.ray_mask_ids:
+            return batch
+        label = batch["label"]
+        keep = torch.ones_like(label, dtype=torch.bool)
+        for i in self.ray_mask_ids:
+            keep &= label != i
+        return {k: (v[keep] if torch.is_tensor(v) and v.shape[:1] == label.shape[:1] else v) for k, v in batch.items()}
+
+    def compute_grads(self, batch):
+        """forward + loss + backward of one batch; every .grad becomes a view of the flat gradient buffer.
+        Returns (detached loss, flat gradient of neuconw+nerf, embedding gradient)."""
+        batch = self.filter_rays(batch)
         rays, rgbs, ts, label = batch["rays"], batch["rgbs"], batch["ts"], batch["label"]
-        ev = getattr(self, "stage_events", None)       # optional [(name, cuda event)] list for stage timing
-        mark = (lambda n: ev.append((n, _rec()))) if ev is not None else (lambda n: None)
-        mark("start")
-        self.renderer.nerf_far_override = False
+        self.renderer.nerf_far_override = False       # training always reads near/far from the cache (neuconw_system.py:345)
         for p in self.params:                  # zero_grad(set_to_none=True)
             p.grad = None
         results = self.forward(rays, ts, label)
-        mark("forward")
+        self._mark("forward")
         loss = sum(self.loss(results, rgbs).values())
         loss.backward()
-        mark("backward")
+        self._mark("backward")
         eng = self.renderer.engine
         flat = eng.last_flat_grad
         for k, p in eng.named_params():        # make every .grad a view of the flat gradient buffer
@@ -143,22 +155,42 @@ class TrainSystem:
             if k.endswith("deviation_network.variance") and p.grad is not None:
                 view.copy_(p.grad)             # reaches the parameter through torch glue (inv_s), not through the engine
             p.grad = view
+        return loss.detach(), flat, self.embedding_a.weight.grad
+
+    def reduce_grads(self, flat, emb_grad):
+        """DDP semantics: gradient MEAN over ranks (per-rank loss normalisers stay per-rank).  One collective
+        for neuconw + nerf (15.6 MB flat buffer, NCCL over NVLink) and one for the dense embedding gradient."""
         if self.world_size > 1:
-            dist.all_reduce(flat)                      # one collective for neuconw + nerf (15 MB, NVLink)
+            dist.all_reduce(flat)
             flat.div_(self.world_size)
-            eg = self.embedding_a.weight.grad
-            if eg is not None:
-                dist.all_reduce(eg)
-                eg.div_(self.world_size)
+            if emb_grad is not None:
+                dist.all_reduce(emb_grad)
+                emb_grad.div_(self.world_size)
+
+    def apply_grads(self, flat, emb_grad):
+        eng = self.renderer.engine
         if self.fused_optimizer:
             # the flat buffers hold every neuconw / nerf parameter (the embedding slice of the table is unused there)
-            self.optimizer.step([(eng.flat, flat), (self.embedding_a.weight.data, self.embedding_a.weight.grad)])
+            self.optimizer.step([(eng.flat, flat), (self.embedding_a.weight.data, emb_grad)])
         else:
             torch.nn.utils.clip_grad_norm_(self.params, 0.99)
             self.optimizer.step()
-        mark("optimizer")
+        self._mark("optimizer")
         self.global_step += 1
-        return loss.detach()
+
+    def _mark(self, name):
+        ev = getattr(self, "stage_events", None)       # optional [(name, cuda event)] list for stage timing
+        if ev is not None:
+            ev.append((name, _rec()))
+
+    def training_step(self, batch):
+        """training_step + backward + DDP-mean all-reduce + clip(0.99) + Adam (neuconw_system.py:337-360,
+        train.py:61).  Returns the detached loss tensor (device)."""
+        self._mark("start")
+        loss, flat, eg = self.compute_grads(batch)
+        self.reduce_grads(flat, eg)
+        self.apply_grads(flat, eg)
+        return loss
 
 
 def _rec():

@@ -28,6 +28,29 @@ COLOR_CONFIG = dict(d_in=9, d_feature=512, mode="idr", d_out=3, d_hidden=256, n_
                     head_channels=128, static_head_layers=2, weight_norm=True, multires_view=4)
 
 
+def install_injected_hits(renderer, hits, device="cpu"):
+    """Config C3 without Kaolin: replace ONLY the Kaolin-backed ``get_near_far`` symbol that
+    ``rendering/renderer.py`` imported (tools/prepare_data/generate_voxel.py:311) by a function returning injected
+    trace results, and hand the renderer two placeholder octree dicts.  The reference's own
+    ``get_near_far_octree`` / ``get_near_far_sdf`` / ``sparse_sampler`` arithmetic (renderer.py:380-568) runs unmodified."""
+    import rendering.renderer as rr  # type: ignore
+
+    coarse_tag, fine_tag = object(), object()
+
+    def fake_get_near_far(rays_o, rays_d, octree, *a, **k):
+        if octree is fine_tag:
+            return hits["surface"].to(rays_o.device).clone(), None
+        assert octree is coarse_tag
+        return hits["sfm_near"].to(rays_o.device).clone(), hits["sfm_far"].to(rays_o.device).clone()
+
+    rr.get_near_far = fake_get_near_far
+    od = lambda tag, extra: dict(octree=tag, scene_origin=torch.zeros(3), scale=1.0, level=1, spc_data=None, **extra)
+    renderer.octree_data = od(coarse_tag, {})
+    renderer.fine_octree_data = od(fine_tag, {"voxel_size": hits["fine_voxel_sfm"]})
+    renderer.nerf_far_override = True
+    renderer.voxel_size = hits["voxel_size"]
+
+
 def build_reference(cfg: synth.PathConfig, P):
     """Construct the reference modules and load the synthetic parameters into them."""
     ref = ref_import.load()
@@ -64,10 +87,12 @@ def build_reference(cfg: synth.PathConfig, P):
     return dict(neuconw=neuconw, nerf=nerf, emb=emb, renderer=renderer, loss=loss)
 
 
-def reference_train_step(cfg, P, batch, perturb_overwrite=0, rand_seed=None):
+def reference_train_step(cfg, P, batch, perturb_overwrite=0, rand_seed=None, hits=None):
     """The reference's own forward/loss/backward (NeuconWSystem.forward semantics,
     lightning_modules/neuconw_system.py:159-176,337-360)."""
     m = build_reference(cfg, P)
+    if hits is not None:
+        install_injected_hits(m["renderer"], hits)
     if rand_seed is not None:
         torch.manual_seed(rand_seed)
     with warnings.catch_warnings():
@@ -103,7 +128,12 @@ CASES = {
     "small_perturb": (synth.PathConfig(n_samples=16, n_importance=16, up_sample_steps=4, n_outside=4,
                                        perturb=1.0, **synth.BRANDENBURG), 48, -1, 123),
     "c1_slice": (synth.C1, 32, 0, None),
+    # config C3: SfM-octree near/far override + surface-guided fine sampling + boundary samples with INJECTED octree
+    # trace results (synth.make_injected_hits), perturbed strata, scene frame
+    "fine_c3": (synth.PathConfig(n_samples=16, n_importance=16, up_sample_steps=4, n_outside=4, perturb=1.0,
+                                 boundary_samples=10, sample_range=8.0, **synth.BRANDENBURG), 48, -1, 321),
 }
+FINE_CASES = {"fine_c3"}
 
 
 def main():
@@ -114,7 +144,8 @@ def main():
     P = synth.make_params(seed=0)
     for name, (cfg, n_rays, pov, rseed) in CASES.items():
         batch = synth.make_rays(n_rays, cfg, seed=11)
-        res, loss, grads, m = reference_train_step(cfg, P, batch, perturb_overwrite=pov, rand_seed=rseed)
+        hits = synth.make_injected_hits(batch, cfg) if name in FINE_CASES else None
+        res, loss, grads, m = reference_train_step(cfg, P, batch, perturb_overwrite=pov, rand_seed=rseed, hits=hits)
         # re-run the sampler alone for z_vals (deterministic given the same torch seed)
         o = ((batch["rays"][:, 0:3] - torch.tensor(cfg.origin, dtype=torch.float64).float()) / cfg.radius).float()
         near, far = (batch["rays"][:, 6:7] / cfg.radius).float(), (batch["rays"][:, 7:8] / cfg.radius).float()
@@ -122,7 +153,7 @@ def main():
             torch.manual_seed(rseed)
         with torch.no_grad():
             _, z, z_out, sd = m["renderer"].sparse_sampler(
-                o, batch["rays"][:, 3:6], near, far, cfg.perturb if pov < 0 else pov)
+                o, batch["rays"][:, 3:6], near.clone(), far.clone(), cfg.perturb if pov < 0 else pov)
         arrays = {f"out.{k}": v.detach().numpy() for k, v in res.items()}
         arrays.update(z_vals=z.numpy(), z_vals_outside=z_out.numpy(), sample_dist=sd.numpy(),
                       loss=loss.numpy())

@@ -157,3 +157,51 @@ def make_perturb_noise(n_rays: int, n_outside: int, seed: int = 7):
     u_ray = torch.rand(n_rays, 1, generator=g)
     u_out = torch.rand(n_rays, max(n_outside, 1), generator=g)[:, :n_outside]
     return u_ray, u_out
+
+
+def make_injected_hits(batch, cfg: PathConfig, voxel_size: float = 0.1, fine_voxel: float = 0.02, seed: int = 3):
+    """Synthetic results of the two octree traces of config C3 (tools/prepare_data/generate_voxel.py:311-439 is
+    Kaolin and cannot run here), INJECTED identically into the reference, the port and the CUDA path:
+
+      sfm_near, sfm_far [R]  first-hit / last-entry depth of the SfM octree in SfM units (0 = miss), the values
+                             get_near_far returns to NeuconWRenderer.get_near_far_octree (renderer.py:392-402)
+      surface [R]            first-hit depth of the SDF-derived octree (0 = miss), returned to get_near_far_sdf
+                             (renderer.py:431-441)
+
+    Geometry: the ray / sphere(|x| = 0.5, unit frame) intersection, jittered; ~1/8 of the hit rays are turned
+    into misses of either octree so both branches of both masks are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    rays = batch["rays"]
+    origin = torch.tensor(cfg.origin, dtype=torch.float64).float()
+    o = (rays[:, 0:3] - origin) / cfg.radius
+    d = rays[:, 3:6]
+    b = (o * d).sum(-1)
+    c = (o * o).sum(-1) - 0.25
+    disc = b * b - c
+    hit = disc > 0
+    t_in = (-b - torch.sqrt(disc.clamp_min(0))) * cfg.radius
+    t_out = (-b + torch.sqrt(disc.clamp_min(0))) * cfg.radius
+    R = rays.shape[0]
+    drop_a = torch.rand(R, generator=g) < 0.125
+    drop_b = torch.rand(R, generator=g) < 0.125
+    jit = (torch.rand(R, generator=g) - 0.5) * voxel_size
+    sfm_near = torch.where(hit & ~drop_a, t_in - 0.2 * cfg.radius + jit, torch.zeros(R))
+    sfm_far = torch.where(hit & ~drop_a, t_out + 0.1 * cfg.radius + jit, torch.zeros(R))
+    surface = torch.where(hit & ~drop_b, t_in - 0.5 * fine_voxel * cfg.radius, torch.zeros(R))
+    return dict(sfm_near=sfm_near.float(), sfm_far=sfm_far.float(), surface=surface.float(), voxel_size=voxel_size,
+                fine_voxel_sfm=float(fine_voxel * cfg.radius))
+
+
+def injected_near_far(hits, cfg: PathConfig, near, far):
+    """renderer.py:380-456 on injected trace results, float32 torch ops in the reference's order:
+    returns (near, far, sample_near, sample_far), all [R,1] in the unit-sphere frame."""
+    vn, vf = hits["sfm_near"].to(near.device), hits["sfm_far"].to(near.device)
+    hit = (vn > 0).reshape(-1, 1)
+    near = torch.where(hit, vn.float().reshape(-1, 1) / cfg.radius, near)
+    far = torch.where(hit, (vf.float().reshape(-1, 1) + hits["voxel_size"]) / cfg.radius, far)
+    surf = hits["surface"].to(near.device).reshape(-1, 1)
+    miss = surf <= 0
+    tvs = hits["fine_voxel_sfm"]
+    s_near = torch.where(miss, near, (surf - cfg.sample_range * tvs).float() / cfg.radius)
+    s_far = torch.where(miss, far, (surf + cfg.sample_range * tvs).float() / cfg.radius)
+    return near, far, s_near, s_far

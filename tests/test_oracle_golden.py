@@ -9,7 +9,7 @@ import torch
 from conftest import GOLDEN
 from oracle import neuconw_port as port
 from oracle import synth
-from oracle.make_golden import CASES, grad_probe
+from oracle.make_golden import CASES, FINE_CASES, grad_probe
 
 RTOL = 1e-4  # north-star tolerance (relative to the tensor's max magnitude)
 
@@ -28,8 +28,8 @@ def test_port_matches_reference_golden(name, params):
     batch = synth.make_rays(n_rays, cfg, seed=11)
     if rseed is not None:
         torch.manual_seed(rseed)
-    extras = {}
-    res, loss, grads = port.train_step(params, cfg, batch, perturb_overwrite=pov)
+    hits = synth.make_injected_hits(batch, cfg) if name in FINE_CASES else None
+    res, loss, grads = port.train_step(params, cfg, batch, perturb_overwrite=pov, hits=hits)
     assert abs(float(loss) - float(G["loss"])) <= 1e-5 * abs(float(G["loss"]))
     for k, v in res.items():
         g = G["out." + k]
@@ -56,7 +56,7 @@ def test_port_sampler_matches_reference_golden(name, params):
     with torch.no_grad():
         port.render(params, cfg, batch["rays"], batch["ts"], batch["label"], perturb_overwrite=pov,
                     background_rgb=torch.zeros(1, 3), cos_anneal_ratio=cfg.cos_anneal_ratio,
-                    extras=extras)
+                    extras=extras, hits=synth.make_injected_hits(batch, cfg) if name in FINE_CASES else None)
     # same torch ops in the same order on the same machine class: bit-identical
     assert np.array_equal(extras["z_vals"].numpy(), G["z_vals"])
     assert np.array_equal(extras["z_vals_outside"].numpy(), G["z_vals_outside"])
