@@ -230,6 +230,33 @@ NRW_API int nrw_adam_clip_step(float* p, const float* grad, float* m, float* v, 
                                double max_norm, double lr, double beta1, double beta2, double eps, int step,
                                void* stream);
 
+/* ---- ray-cache batch gather: PhototourismDataset.__getitem__ with semantics over an index vector
+ *      (datasets/phototourism.py:709-724) fused with training_step's RAY_MASK_LIST filter
+ *      (lightning_modules/neuconw_system.py:345-355).  cache_rays [n,12] = o3,d3,near,far,ts,label,depth,weight and
+ *      cache_rgbs [n,3] are the reference's cache arrays (tools/prepare_data/prepare_data_cache.py:128-151) resident in HBM.
+ *      Rows whose label equals one of mask_labels_host[0..n_mask) (<= 8 ids, host array) are dropped; kept rows are
+ *      written in index order: rays [m,10] = row[0:8] ++ row[10:12], rgbs [m,3], ts [m] int64, label [m]; n_valid[0] = m
+ *      (device int64).  scratch: nrw_compact_scratch_bytes(batch) bytes, 256-byte aligned. ---------------------------- */
+NRW_API long long nrw_compact_scratch_bytes(long long n);
+NRW_API int nrw_raycache_gather(const float* cache_rays, const float* cache_rgbs, long long n_cache, const int64_t* index,
+                                int batch, const int32_t* mask_labels_host, int n_mask, float* rays, float* rgbs, int64_t* ts,
+                                float* label, int64_t* n_valid, void* scratch, void* stream);
+/* ---- mesh-extraction / octree-refresh query pipeline ------------------------------------------------
+ * dense lattice of utils/visualization.py:42-52: out[t] = (lin_x[i], lin_y[j], lin_z[k]) for linear index i0+t =
+ * (i*dim + j)*dim + k, lin_c = torch.linspace(lo[c], hi[c], dim) (float32). */
+NRW_API int nrw_grid_points_dense(int dim, const float lo[3], const float hi[3], long long i0, long long n, float* out /*[n,3]*/,
+                                  void* stream);
+/* up-sampled sparse lattice of tools/extract_mesh.py:73-95 / neuconw_system.py:213-234: candidate i0+t -> leaf (i0+t)/up^3
+ * (leaves int16 [n_leaves,3], lexicographic = torch.nonzero order), sub-voxel unravel((i0+t)%up^3); xyz_sfm (optional) =
+ * float32(index)*voxel_size + vol_origin, xyz_train = (xyz_sfm - scene_origin)/scene_radius. */
+NRW_API int nrw_grid_points_sparse(const int16_t* leaves, long long n_leaves, int up_times, float voxel_size,
+                                   const float vol_origin[3], const float scene_origin[3], float scene_radius, long long i0,
+                                   long long n, float* xyz_sfm, float* xyz_train, void* stream);
+/* stable compaction xyz[sdf <= threshold] (neuconw_system.py:259), appended at out[count[0]...]; count (device int64) is
+ * increased by the number of rows kept.  scratch: nrw_compact_scratch_bytes(n). */
+NRW_API int nrw_threshold_compact(const float* sdf, const float* xyz /*[n,3]*/, long long n, float threshold, float* out,
+                                  int64_t* count, void* scratch, void* stream);
+
 /* ---- unit-test hooks ---------------------------------------------------------------------- */
 /* D[M,N] = (sum planes of A)[M,K] * (sum planes of B)[N,K]^T from fp32 inputs: splits into planes in
  * scratch (caller-provided, nrw_gemm_test_scratch_bytes) and runs the selected backend. */
@@ -239,9 +266,10 @@ NRW_API int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices,
                           void* scratch, void* stream);
 NRW_API long long nrw_launch_count(void);
 /* measurement: while enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its stream; a call with
- * out4 != NULL synchronises those events and returns {sum of kernel ms, algorithmic FLOP (2MNK), MMA FLOP
- * (x plane products), launches} since the last read (bench.py roofline). */
-NRW_API int nrw_gemm_timing(int enable, double* out4_host);
+ * out5 != NULL synchronises those events and returns {sum of kernel ms, algorithmic FLOP (2MNK), MMA FLOP
+ * (x plane products), launches, algorithmic HBM bytes (operands + epilogue streams)} since the last read
+ * (bench.py roofline). */
+NRW_API int nrw_gemm_timing(int enable, double* out5_host);
 /* debug: per-CTA cycle attribution of the tcgen05 GEMM (u64 [SMs,16], zeroed by the caller; NULL = off) */
 NRW_API int nrw_debug_gemm_profile(void* device_buf_u64);
 

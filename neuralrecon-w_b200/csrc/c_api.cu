@@ -274,6 +274,40 @@ int nrw_adam_clip_step(float* p, const float* grad, float* m, float* v, long lon
   NRW_GUARD_END
 }
 
+long long nrw_compact_scratch_bytes(long long n) { return compact_scratch_bytes(n); }
+int nrw_raycache_gather(const float* cache_rays, const float* cache_rgbs, long long n_cache, const int64_t* index, int batch,
+                        const int32_t* mask_labels_host, int n_mask, float* rays, float* rgbs, int64_t* ts, float* label,
+                        int64_t* n_valid, void* scratch, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(batch == 0 || (cache_rays && cache_rgbs && index && rays && rgbs && ts && label && n_valid && scratch), NRW_ERR_ARG,
+            "nrw_raycache_gather: null pointer");
+  return raycache_gather(cache_rays, cache_rgbs, n_cache, index, batch, mask_labels_host, n_mask, rays, rgbs, ts, label, n_valid,
+                         scratch, S(stream));
+  NRW_GUARD_END
+}
+int nrw_threshold_compact(const float* sdf, const float* xyz, long long n, float threshold, float* out, int64_t* count,
+                          void* scratch, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(n == 0 || (sdf && xyz && out && count && scratch), NRW_ERR_ARG, "nrw_threshold_compact: null pointer");
+  return threshold_compact(sdf, xyz, n, threshold, out, count, scratch, S(stream));
+  NRW_GUARD_END
+}
+int nrw_grid_points_dense(int dim, const float lo[3], const float hi[3], long long i0, long long n, float* out, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(n == 0 || (lo && hi && out), NRW_ERR_ARG, "nrw_grid_points_dense: null pointer");
+  return grid_points_dense(dim, lo, hi, i0, n, out, S(stream));
+  NRW_GUARD_END
+}
+int nrw_grid_points_sparse(const int16_t* leaves, long long n_leaves, int up_times, float voxel_size, const float vol_origin[3],
+                           const float scene_origin[3], float scene_radius, long long i0, long long n, float* xyz_sfm,
+                           float* xyz_train, void* stream) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(n == 0 || (leaves && vol_origin && scene_origin && xyz_train), NRW_ERR_ARG, "nrw_grid_points_sparse: null pointer");
+  return grid_points_sparse(leaves, n_leaves, up_times, voxel_size, vol_origin, scene_origin, scene_radius, i0, n, xyz_sfm, xyz_train,
+                            S(stream));
+  NRW_GUARD_END
+}
+
 long long nrw_gemm_test_scratch_bytes(int M, int N, int K) {
   const long long a = round_up((long long)M * K, 512), b = round_up((long long)N * K, 512);
   return (a + b) * 3 * 2 + 4096;
@@ -301,12 +335,12 @@ int nrw_gemm_test(int backend, int n_planes, int mn_major, int k_slices, int M, 
   NRW_GUARD_END
 }
 long long nrw_launch_count(void) { return g_kernel_launches; }
-int nrw_gemm_timing(int enable, double* out4 /* host: ms, algorithmic FLOP, MMA FLOP, launches; may be NULL */) {
+int nrw_gemm_timing(int enable, double* out5 /* host: ms, algorithmic FLOP, MMA FLOP, launches, algorithmic HBM bytes; may be NULL */) {
   NRW_GUARD_BEGIN
-  if (out4) {
+  if (out5) {
     long long n = 0;
-    NRW_TRY(gemm_tc_timing_read(&out4[0], &out4[1], &out4[2], &n));
-    out4[3] = (double)n;
+    NRW_TRY(gemm_tc_timing_read(&out5[0], &out5[1], &out5[2], &n, &out5[4]));
+    out5[3] = (double)n;
   }
   gemm_tc_timing_enable(enable != 0);
   return NRW_OK;

@@ -33,6 +33,6 @@ long long gemm_tc_launch_count();
 void gemm_tc_set_profile_buffer(unsigned long long* buf);
 // measurement: CUDA events around every tcgen05 GEMM launch (on the launching stream)
 void gemm_tc_timing_enable(bool on);
-int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches);
+int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches, double* bytes);
 
 }  // namespace nrw

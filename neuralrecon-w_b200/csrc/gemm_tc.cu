@@ -764,8 +764,8 @@ static cudaEvent_t get_event() {
   return e;
 }
 // sums (and clears) the recorded launches: total kernel ms, algorithmic FLOP (2MNK), MMA FLOP (x products), count
-int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches) {
-  double t = 0, f = 0, mf = 0;
+int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long* launches, double* bytes) {
+  double t = 0, f = 0, mf = 0, by = 0;
   // tuning: NRW_GEMM_TIMING_DUMP=<path> appends one CSV row per launch: M,N,K,planes,mn_major,k_slices,epilogue bits,
   // algorithmic bytes,ms   (bits: 1 out_pre 2 out_f32 4 out2 8 planes 16 aux_sig 32 aux_q 64 aux_add 128 aux_relu 256 atomic 512 colsum)
   FILE* dump = getenv("NRW_GEMM_TIMING_DUMP") ? fopen(getenv("NRW_GEMM_TIMING_DUMP"), "a") : nullptr;
@@ -773,12 +773,13 @@ int gemm_tc_timing_read(double* ms, double* flops, double* mma_flops, long long*
     NRW_CUDA_OK(cudaEventSynchronize(L.e1));
     float dt = 0;
     NRW_CUDA_OK(cudaEventElapsedTime(&dt, L.e0, L.e1));
-    t += dt; f += L.flops; mf += L.mma_flops;
+    t += dt; f += L.flops; mf += L.mma_flops; by += L.bytes;
     g_event_pool.push_back(L.e0); g_event_pool.push_back(L.e1);
     if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%u,%.0f,%.4f\n", L.M, L.N, L.K, L.P, L.mn, L.ks, L.epi, L.bytes, dt);
   }
   if (dump) fclose(dump);
   *ms = t; *flops = f; *mma_flops = mf; *launches = (long long)g_timed.size();
+  if (bytes) *bytes = by;
   g_timed.clear();
   return NRW_OK;
 }

@@ -24,3 +24,18 @@ int grad_sumsq(const float* g, long long n, double* acc, cudaStream_t s);
 int adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const double* sumsq, double max_norm, double lr,
                    double b1, double b2, double eps, int step, cudaStream_t s);
 }  // namespace nrw
+
+// data movers either side of the hot path (dataio.cu): ray-cache batch gather + label filter, query-point generators of
+// the mesh-extraction / octree-refresh pipelines, stable threshold compaction
+namespace nrw {
+long long compact_scratch_bytes(long long n);
+int raycache_gather(const float* cache_rays, const float* cache_rgbs, long long n_cache, const int64_t* index, int batch,
+                    const int32_t* mask_labels, int n_mask, float* rays, float* rgbs, int64_t* ts, float* label,
+                    int64_t* n_valid, void* scratch, cudaStream_t s);
+int threshold_compact(const float* sdf, const float* xyz, long long n, float thr, float* out, int64_t* count, void* scratch,
+                      cudaStream_t s);
+int grid_points_dense(int dim, const float lo[3], const float hi[3], long long i0, long long n, float* out, cudaStream_t s);
+int grid_points_sparse(const int16_t* leaves, long long n_leaves, int up, float voxel, const float vol_origin[3],
+                       const float scene_origin[3], float scene_radius, long long i0, long long n, float* xyz_sfm,
+                       float* xyz_train, cudaStream_t s);
+}  // namespace nrw

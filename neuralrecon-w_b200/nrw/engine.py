@@ -149,7 +149,9 @@ class Engine:
         torch bumps the version counter of the flat buffer on every in-place update of a view (optimizer.step,
         load_state_dict, .copy_), FusedClipAdam bumps it explicitly after writing through the raw pointer."""
         named = self.flatten(device)
-        token = (self.flat.data_ptr(), self.flat._version)
+        # (a Parameter whose .data was re-pointed at a slice of the flat buffer keeps its OWN version counter, so the
+        # per-parameter counters are part of the token: torch.optim.* steps bump those, not the flat buffer's)
+        token = (self.flat.data_ptr(), self.flat._version, sum(p._version for _, p in named))
         if getattr(self, "packed_version", None) != token:
             check(self.L.nrw_pack_weights(self.ctx, ptr(self.flat), stream_ptr()), "nrw_pack_weights")
             self.packed_version = token

@@ -114,47 +114,24 @@ def level_for_voxel(scale, voxel_size):
 # ---- octree refresh (lightning_modules/neuconw_system.py:186-312), device resident -------------------------------
 def surface_selection(renderer, train_level, threshold, device=0, chunk=1 << 20, sdf_fn=None):
     """neuconw_system.py:186-266.  The reference densifies the coarse octree, moves it to the CPU, builds the candidate
-    list with numpy-style torch ops and ships chunks back to the GPU; here the level-L leaves are taken straight from
-    the point hierarchy (lexicographic order = torch.nonzero(dense)), candidates are generated on the GPU in the same
-    dtypes (int64 index * python float -> float32) and the SDF runs through nrw_sdf_query.  `sdf_fn(xyz_training)`
-    overrides the network (tests).  Returns (sparse_pc_sfm float32 CUDA [m,3], train_voxel_size)."""
-    if renderer.octree_data is None:
-        renderer.octree_data = renderer.get_octree(device)
-    od = renderer.octree_data
-    spc = od["spc_data"]
-    dev = od["octree"].device
-    L0 = int(od["level"])
-    pyr = spc["pyramid"]
-    leaves = spc["points"][int(pyr[1, L0]):int(pyr[1, L0 + 1])].to(torch.int64)
-    key = (leaves[:, 0] * (1 << L0) + leaves[:, 1]) * (1 << L0) + leaves[:, 2]
-    sparse_ind = leaves[torch.argsort(key)]
-    sparse_num = sparse_ind.shape[0]
-    up_times = 2 ** (int(train_level) - L0)
-    if up_times < 1:
-        raise NrwError(f"surface_selection: train_level {train_level} below the octree level {L0}")
-    k = torch.arange(0, up_times, 1, device=dev)
-    up_kernal = torch.stack(torch.meshgrid(k, k, k, indexing="ij"), dim=-1).reshape(-1, 3)
-    sparse_ind_up = sparse_ind.repeat_interleave(up_times ** 3, dim=0) * up_times + up_kernal.repeat([sparse_num, 1])
-    octree_scale = od["scale"]
-    train_voxel_size = 2 / (2 ** int(train_level)) * octree_scale
-    vol_origin = od["scene_origin"].float().to(dev) - octree_scale
-    xyz_sfm = sparse_ind_up * train_voxel_size + vol_origin
-    origin = torch.as_tensor(renderer.origin).float().to(dev)
-    xyz_training = (xyz_sfm - origin) / renderer.radius
-    if sdf_fn is None:
-        out = []
-        for i in range(0, xyz_training.shape[0], chunk):
-            out.append(renderer.sdf(xyz_training[i:i + chunk].reshape(-1, 1, 3)).detach().reshape(-1))
-        sdf = torch.cat(out) if out else torch.zeros(0, device=dev)
-    else:
-        sdf = sdf_fn(xyz_training).reshape(-1)
-    return xyz_sfm[sdf <= threshold], train_voxel_size
+    list with numpy-style torch ops, ships chunks to the GPU and every SDF chunk back; here the level-L leaves are taken
+    straight from the point hierarchy (lexicographic order = torch.nonzero(dense)), candidate points are GENERATED on the
+    GPU chunk by chunk in the same dtypes (nrw_grid_points_sparse: int64 index * python float -> float32), the SDF runs
+    through nrw_sdf_query, ranks evaluate the contiguous slices of get_local_split and all-gather them
+    (neuconw_system.py:236-258), and `xyz_sfm[sdf <= threshold]` is a stable device-side compaction.
+    `sdf_fn(xyz_training)` overrides the network (tests).  Returns (sparse_pc_sfm float32 CUDA [m,3], train_voxel_size)."""
+    from .mesh import gen_grid_spc, sparse_candidates
+
+    grid = gen_grid_spc(renderer, train_level, device)
+    res = sparse_candidates(renderer, grid, chunk=chunk, threshold=threshold, sdf_fn=sdf_fn, want_sdf=False)
+    return res["kept_xyz_sfm"], grid["voxel_size"]
 
 
 def octree_update(renderer, train_level, threshold, device=0, chunk=1 << 20, sdf_fn=None):
     """neuconw_system.py:268-312: installs renderer.fine_octree_data built from the current SDF (needs
-    renderer.scene_config, as get_octree does).  Every rank evaluates the full candidate list (the reference splits it
-    across ranks and all-gathers; the result is identical and the list is small next to a training step)."""
+    renderer.scene_config, as get_octree does).  With torch.distributed initialised the candidate SDFs are split across
+    ranks and all-gathered exactly as the reference does (neuconw_system.py:236-258); every rank then builds the same
+    octree."""
     cfg = getattr(renderer, "scene_config", None)
     if cfg is None:
         raise NrwError("octree_update: set renderer.scene_config (sfm2gt, eval_bbx of the scene's config.yaml)")

@@ -34,3 +34,25 @@ def make_ray_batch(n_rays, origin=(0.0, 0.0, 0.0), radius=1.0, n_vocab=5000, see
     if device != "cpu":
         out = {k: v.to(device) for k, v in out.items()}
     return out
+
+
+def sphere_shell_points(radius=0.5, thickness=0.05, n=20000, seed=0):
+    """Synthetic SfM point cloud: points in the shell | |x| - radius | < thickness (stands in for COLMAP's
+    points3D.bin of a real scene)."""
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    v = v / v.norm(dim=-1, keepdim=True)
+    return v * (radius + (torch.rand(n, 1, generator=g, dtype=torch.float64) * 2 - 1) * thickness)
+
+
+def install_synthetic_scene(renderer, radius=1.0, origin=(0.0, 0.0, 0.0), voxel_size=0.1, n_points=20000, seed=0):
+    """What NeuconWSystem / get_octree read from <ROOT_DIR>/config.yaml and points3D.bin (neuconw_system.py:65-67,
+    generate_voxel.py:41-73), synthesised: scene frame, eval bounding box, SfM point cloud."""
+    import numpy as np
+
+    r = float(radius)
+    renderer.scene_config = {"sfm2gt": np.eye(4).tolist(),
+                             "eval_bbx": [[origin[0] - r, origin[1] - r, origin[2] - r], [origin[0] + r, origin[1] + r, origin[2] + r]]}
+    renderer.sfm_points = (sphere_shell_points(0.5 * r, 0.03 * r, n_points, seed) + torch.tensor(origin, dtype=torch.float64)).numpy()
+    renderer.voxel_size = voxel_size * r
+    return renderer

@@ -145,6 +145,11 @@ class TrainSystem:
         results = self.forward(rays, ts, label)
         self._mark("forward")
         loss = sum(self.loss(results, rgbs).values())
+        if getattr(self, "track_metrics", False):      # device tensors, no host sync (neuconw_system.py:362-371 logs the same)
+            with torch.no_grad():
+                mse = ((results["color"].detach() - rgbs) ** 2).mean()
+                self.last_metrics = {"loss": loss.detach(), "psnr": -10.0 * torch.log10(mse),
+                                     "eikonal": results["gradient_error"].detach().mean(), "s_val": results["s_val"].detach().mean()}
         loss.backward()
         self._mark("backward")
         eng = self.renderer.engine

@@ -61,16 +61,103 @@ def _install_stubs():
             pl = types.ModuleType("pytorch_lightning")
 
             class LightningModule(torch.nn.Module):
-                def save_hyperparameters(self, *a, **k):
-                    pass
+                """the slice of pytorch_lightning.LightningModule NeuconWSystem touches (neuconw_system.py)"""
 
-                def log(self, *a, **k):
-                    pass
+                def __init__(self, *a, **k):
+                    super().__init__()
+                    self.global_step = 0
+                    self.logged = {}
+                    self.trainer = types.SimpleNamespace(global_rank=0, save_checkpoint=lambda *a, **k: None)
+                    self.logger = types.SimpleNamespace(save_dir="/tmp", name="nrw", experiment=mock.MagicMock())
+
+                def save_hyperparameters(self, hparams=None, *a, **k):
+                    self.hparams = hparams
+
+                def log(self, name, value, *a, **k):
+                    self.logged[name] = value
+
+                @property
+                def device(self):
+                    return next(self.parameters()).device
 
             pl.LightningModule = LightningModule
             pl.LightningDataModule = object
             pl.seed_everything = lambda s: torch.manual_seed(s)
             sys.modules["pytorch_lightning"] = pl
+
+
+class CfgNode(dict):
+    """Minimal yacs.config.CfgNode (attribute access, clone, merge_from_file with literal evaluation of strings such
+    as "(4,)") for config/defaults.py when yacs is not installed."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def clone(self):
+        import copy
+        return copy.deepcopy(self)
+
+    def _merge(self, other):
+        import ast
+        for k, v in other.items():
+            if isinstance(v, dict):
+                node = self.get(k)
+                if not isinstance(node, CfgNode):
+                    node = self[k] = CfgNode()
+                node._merge(v)
+            else:
+                if isinstance(v, str):
+                    try:
+                        v = ast.literal_eval(v)
+                    except (ValueError, SyntaxError):
+                        pass
+                self[k] = v
+
+    def merge_from_file(self, path):
+        import yaml
+        with open(path, "r") as f:
+            self._merge(yaml.safe_load(f))
+
+
+def _install_yacs():
+    try:
+        import yacs.config  # noqa: F401
+        if not isinstance(sys.modules.get("yacs"), mock.MagicMock):
+            return
+    except Exception:
+        pass
+    y, yc = types.ModuleType("yacs"), types.ModuleType("yacs.config")
+    yc.CfgNode = CfgNode
+    y.config = yc
+    sys.modules["yacs"], sys.modules["yacs.config"] = y, yc
+
+
+def load_system():
+    """The reference's LightningModule (lightning_modules/neuconw_system.py) and config defaults, importable without
+    pytorch_lightning / yacs / kaolin: returns a namespace with the module `ns` (so callers can re-bind
+    ns.NeuconW / ns.NeRF / ns.NeuconWRenderer / ns.gen_octree ... - the documented drop-in patch), NeuconWSystem,
+    get_cfg_defaults and load_ckpt (utils/__init__.py:64-98)."""
+    if not available():
+        raise RuntimeError(f"reference tree not present at {REF_ROOT}")
+    _install_yacs()
+    _install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import lightning_modules.neuconw_system as ns  # type: ignore
+        from config.defaults import get_cfg_defaults  # type: ignore
+        from utils import load_ckpt  # type: ignore
+    return types.SimpleNamespace(ns=ns, NeuconWSystem=ns.NeuconWSystem, get_cfg_defaults=get_cfg_defaults, load_ckpt=load_ckpt,
+                                 config_dir=os.path.join(REF_ROOT, "config"))
 
 
 def load():

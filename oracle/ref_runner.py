@@ -42,6 +42,10 @@ class RefRunner:
                                        background_rgb=torch.zeros([1, 3], device=self.device),
                                        cos_anneal_ratio=cfg.cos_anneal_ratio)
             loss = sum(m["loss"](res, batch["rgbs"]).values())
+            with torch.no_grad():
+                mse = ((res["color"].detach() - batch["rgbs"]) ** 2).mean()
+                self.last_metrics = {"loss": loss.detach(), "psnr": -10.0 * torch.log10(mse),
+                                     "eikonal": res["gradient_error"].detach().mean(), "s_val": res["s_val"].detach().mean()}
             loss.backward()
         if self.optimizer is not None:
             torch.nn.utils.clip_grad_norm_(self.params, 0.99)

@@ -97,6 +97,8 @@ def test_weights_are_packed_once_per_parameter_version():
     sysm.training_step(b)
     eng = sysm.renderer.engine
     # pack() must be a no-op while the parameter version token is unchanged
+    with torch.no_grad():
+        sysm.forward(b["rays"], b["ts"], b["label"])         # first use after the optimizer step: packs
     tok0 = eng.packed_version
     n0 = eng.L.nrw_launch_count()
     with torch.no_grad():

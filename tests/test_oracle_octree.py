@@ -45,3 +45,22 @@ def test_gen_octree_and_refresh_shapes():
     near, far, pid, cnt = op.get_near_far(new_tree, l2, np.array([[-2.0, 0.01, 0.02]], np.float32), np.array([[1.0, 0, 0]], np.float32),
                                           o2.astype(np.float32), np.float32(s2))
     assert cnt[0] >= 2 and 1.3 < near[0] < 1.7 and 2.3 < far[0] < 2.7
+
+
+def test_octree_to_spc_decoder_matches_restatement():
+    """nrw.generate_voxel.octree_to_spc (torch decode of the child-mask bytes; stand-in for Kaolin's scan_octrees +
+    generate_points with the reference's signature, generate_voxel.py:173-178) vs the restatement's tables."""
+    import torch
+    from nrw.generate_voxel import convert_to_dense, octree_to_spc
+
+    for level, seed in ((5, 2), (7, 3)):
+        pts = op.sphere_shell_points(0.55, 0.05, n=3000, seed=seed)
+        t = op.build_octree(pts, level)
+        points, pyramid, prefix = octree_to_spc(torch.from_numpy(t["octree"].astype(np.uint8)))
+        assert np.array_equal(points.numpy(), t["points"].astype(np.int16))
+        assert np.array_equal(pyramid.numpy(), t["pyramid"].astype(np.int32))
+        assert np.array_equal(prefix.numpy(), t["prefix"].astype(np.int32))
+        dense = convert_to_dense(torch.from_numpy(t["octree"].astype(np.uint8)), level)
+        leaves = t["points"][t["pyramid"][1, level]:t["pyramid"][1, level + 1]]
+        assert dense.shape == (2 ** level,) * 3 and int(dense.sum()) == len(leaves)
+        assert bool((dense[leaves[:, 0], leaves[:, 1], leaves[:, 2]] == 1).all())

@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 L.nrw_gemm_timing(1, None)
 for _ in range(5): call()
 torch.cuda.synchronize()
-out = (C.c_double * 4)()
+out = (C.c_double * 5)()
 L.nrw_gemm_timing(0, out)
 ms = out[0] / out[3]
 print(f"DBG={os.environ.get('NRW_TC_DBG','0')} LAYER={os.environ.get('NRW_GEMM_TEST_LAYER','0')} M={M} N={N} K={K} P={planes} act={act}: {ms*1e3:.1f} us/launch  mma {out[2]/out[0]/1e9:.0f} TF/s")

@@ -26,7 +26,7 @@ t0 = time.time()
 while time.time() - t0 < 1.5:
     for _ in range(50): call()
     torch.cuda.synchronize()
-out = (C.c_double * 4)(); L.nrw_gemm_timing(0, out)
+out = (C.c_double * 5)(); L.nrw_gemm_timing(0, out)
 stop.set(); th.join()
 clk.sort(); pw.sort()
 print(f"DBG={os.environ.get('NRW_TC_DBG','0')} LAYER={os.environ.get('NRW_GEMM_TEST_LAYER','0')} P={planes}: {out[0]/out[3]*1e3:.1f} us/launch over {int(out[3])} launches; "
