@@ -106,7 +106,7 @@ class Engine:
         b = self.bound
         want_chunk = min(self.chunk_rows, ((max(int(chunk_hint), 0) + 127) // 128) * 128)
         if (self.workspace is not None and self.workspace.device == device and b[0] >= int(max_rays) and b[1] >= int(max_T)
-                and b[2] >= int(with_backward) and b[3] >= want_chunk):
+                and b[2] >= int(with_backward) and b[3] >= min(want_chunk, 65536)):     # any bound chunk >= 64k rows serves a query
             return
         max_rays = max(int(max_rays), 1, b[0])
         max_T = max(int(max_T), 2, b[1])
@@ -125,13 +125,19 @@ class Engine:
             ns_sdf = ns_nerf = 1
             if with_backward and os.environ.get("NRW_RECOMPUTE", "0") != "1":
                 S_eff = getattr(self, "bound_S", 0) or max_T
-                want_sdf = -(-max_rays // max(chunk // S_eff, 1))
-                want_nerf = -(-max_rays // max(chunk // max_T, 1))
                 free, _total = torch.cuda.mem_get_info(device)
-                budget = float(os.environ.get("NRW_SLOT_BUDGET_GB", 0)) * 2 ** 30 or 0.6 * free
-                need = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T, want_sdf, want_nerf)
-                if need <= budget:
-                    ns_sdf, ns_nerf = want_sdf, want_nerf
+                budget = float(os.environ.get("NRW_SLOT_BUDGET_GB", 0)) * 2 ** 30 or 0.7 * free
+                # candidate chunk sizes: the configured one, then a BALANCED one (equal rays per chunk, no nearly-empty
+                # last chunk: e.g. 8192 rays x 142 samples = 4.4 chunks of 262144 rows -> 5 chunks of 232,832 rows)
+                n_chunks = -(-(max_rays * max_T) // chunk)
+                balanced = ((-(-max_rays // n_chunks) * max_T + 127) // 128) * 128
+                for cand in ([chunk, balanced] if balanced < chunk else [chunk]):
+                    want_sdf = -(-max_rays // max(cand // S_eff, 1))
+                    want_nerf = -(-max_rays // max(cand // max_T, 1))
+                    need = self.L.nrw_workspace_bytes(self.ctx, cand, with_backward, max_rays, max_T, want_sdf, want_nerf)
+                    if need <= budget:
+                        chunk, ns_sdf, ns_nerf = cand, want_sdf, want_nerf
+                        break
             wb = self.L.nrw_workspace_bytes(self.ctx, chunk, with_backward, max_rays, max_T, ns_sdf, ns_nerf)
             self.workspace = torch.empty(wb + 2048, dtype=torch.uint8, device=device)
             pk = (self.packed.data_ptr() + 1023) // 1024 * 1024
