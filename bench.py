@@ -26,7 +26,8 @@ import torch.distributed as dist  # noqa: E402
 
 # algorithmic FLOP per sample (2*MAC, forward) of the three MLPs (SURVEY.md 8 / BASELINE.md 3)
 F_SDF, F_COL, F_NERF = 4195328, 1170688, 1318912
-DEFAULT_PRECISION = "bf16x3"     # headline precision policy (DESIGN.md 'precision policy')
+DEFAULT_PRECISION = "mixed"      # headline precision policy: 3-product forward (outputs 1e-4), plain-bf16 backward GEMMs (DESIGN.md 6a;
+                                 # evidence: tests/test_gpu_precision_policy.py, profiles/r2_precision_study.json)
 WORKLOADS = {
     "C3": dict(n_samples=64, n_importance=64, up_sample_steps=4, n_outside=4, rays=8192, fine=True, boundary_samples=10, sample_range=16,
                name="brandenburg_gate config + appearance embedding + surface-guided fine sampling (SDF-derived octree traced every step, "
