@@ -68,6 +68,9 @@ NRW_API int nrw_ctx_destroy(nrw_ctx* ctx);
 /* mixed precision: the backward GEMMs use only the first n operand planes (0 = same as forward).  n = 1 with
  * n_planes = 2 keeps every rendered output at split-bf16 accuracy and computes gradients in plain bf16. */
 NRW_API int nrw_ctx_set_backward_planes(nrw_ctx* ctx, int n);
+/* planes of the stored softplus outputs read by the BACKWARD sweeps to rebuild the gates softplus'(a), softplus''(a)
+ * (0 = all forward planes; 1 halves that stream at ~1e-3 relative gate error).  The forward gradient chain always reads all. */
+NRW_API int nrw_ctx_set_backward_gate_planes(nrw_ctx* ctx, int n);
 NRW_API long long nrw_packed_bytes(const nrw_ctx* ctx);
 /* n_slots_sdf / n_slots_nerf: how many chunks keep their forward activations resident for the backward pass
  * (>= number of chunks of a batch: no forward recompute in backward; 1: recompute, minimum memory). */

@@ -66,6 +66,13 @@ int nrw_ctx_set_backward_planes(nrw_ctx* ctx, int n) {
   return NRW_OK;
   NRW_GUARD_END
 }
+int nrw_ctx_set_backward_gate_planes(nrw_ctx* ctx, int n) {
+  NRW_GUARD_BEGIN
+  NRW_CHECK(ctx != nullptr && n >= 0 && n <= ctx->n_planes, NRW_ERR_ARG, "set_backward_gate_planes: n=%d outside 0..n_planes", n);
+  ctx->bwd_gate_planes = n;
+  return NRW_OK;
+  NRW_GUARD_END
+}
 int nrw_ctx_destroy(nrw_ctx* ctx) {
   delete ctx;
   return NRW_OK;

@@ -92,6 +92,17 @@ __device__ __forceinline__ void softplus100_d12(float v, float& d1, float& d2) {
   d1 = s;
   d2 = fsel(t > 20.0f, 0.0f, 100.0f * s * (1.0f - s));
 }
+// The same two derivatives from the softplus OUTPUT u = softplus100(v) (what the forward pass keeps as bf16 planes), so
+// the fp32 pre-activation never has to be stored:  exp(-100 u) = 1 / (1 + exp(100 v)) = 1 - sigmoid(100 v), hence
+//   d1 = 1 - exp(-100 u)   (series below 100 u = 0.02: 1 - e cancels),   d2 = 100 d1 (1 - d1) = 100 d1 exp(-100 u).
+// Above the threshold (100 v > 20) the forward stored u = v, so 100 u > 20 reproduces torch's d1 = 1, d2 = 0 branch.
+__device__ __forceinline__ void softplus100_d12_from_u(float u, float& d1, float& d2) {
+  const float x = fminf(100.0f * u, 80.0f);
+  const float e = mufu_ex2(-x * 1.44269504088896341f);
+  const float ser = x * (1.0f - x * (0.5f - x * 0.16666667f));
+  d1 = fsel(x < 0.02f, ser, 1.0f - e);
+  d2 = fsel(x > 20.0f, 0.0f, 100.0f * d1 * e);
+}
 __device__ __forceinline__ float softplus100_d2(float v) {  // d2 softplus / dv2
   float d1, d2;
   softplus100_d12(v, d1, d2);

@@ -41,7 +41,6 @@ static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, in
     s.PTS = cv.f32(M * 3);
     s.U0 = cv.planes(M, 64, P);
     for (int l = 1; l <= 8; ++l) s.U[l] = cv.planes(M, 512, P);
-    for (int l = 0; l < 8; ++l) s.A[l] = cv.f32(M * 512);
     for (int l = 0; l < 8; ++l) s.G[l] = cv.planes(M, 512, P);
     s.Q[0] = cv.f32(M * 64);
     for (int l = 1; l < 8; ++l) s.Q[l] = cv.f32(M * 512);
@@ -175,6 +174,13 @@ static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t
 static int bias_grad(nrw_ctx& c, Planes dY, int M, int layer, cudaStream_t s) {
   return launch_colsum(dY, c.cur_planes, nullptr, 0, M, c.pm.layers[layer].Np, nullptr, c.db(layer), nullptr, s);
 }
+// gate of SDF layer l (softplus'(a_l), softplus''(a_l)) from the planes of u_{l+1} = softplus(a_l): U[l+1] holds
+// softplus(a_l) (x 1/sqrt2 in its first 473 columns for l == 3, the skip layer's input)
+static void gate_from(nrw_ctx& c, Epi& e, int l, int planes) {
+  e.aux_u = c.U[l + 1];
+  e.aux_u_planes = planes;
+  e.aux_u_scale = (l == 3) ? 1.41421356237309504880f : 1.0f;
+}
 static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld, P.pstride, P.ld}; }
 
 // ---------------------------------------------------------------------------------------------
@@ -188,14 +194,15 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
     Epi e;
     e.bias = c.bias(L_SDF0 + l);
     e.act = ACT_SOFTPLUS100;
-    if (need_normal || l == 7) { e.out_pre = c.A[l]; e.ld_pre = 512; }
+    // (no fp32 pre-activation store: every later gate softplus'(a_l), softplus''(a_l) is recomputed from the planes of
+    //  u_{l+1} = softplus(a_l) that the next layer needs anyway - common.cuh softplus100_d12_from_u)
     e.out_pl = c.U[l + 1];
     if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
     NRW_TRY(mm(c, l == 0 ? c.U0 : c.U[l], c.W(L_SDF0 + l), M, 512, l == 0 ? 64 : 512, e, s));
   }
   const float* w0 = c.f_area + c.pm.heads.sdf_w0;
   const float* b0 = c.f_area + c.pm.heads.sdf_b0;
-  NRW_TRY(launch_sdf_head(c.A[7], M, w0, b0, c.c_sdf, P, need_normal ? c.G[7] : Planes{nullptr, 0, 0}, s));
+  NRW_TRY(launch_sdf_head(c.U[8], M, w0, b0, c.c_sdf, P, need_normal ? c.G[7] : Planes{nullptr, 0, 0}, s));
   if (need_feat) {
     Epi e;
     e.bias = c.bias(L_SDF8F);
@@ -206,7 +213,7 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
     for (int l = 7; l >= 1; --l) {
       Epi e;
       e.out_pre = c.Q[l]; e.ld_pre = 512;
-      e.aux_sig = c.A[l - 1]; e.ld_aux = 512;
+      gate_from(c, e, l - 1, c.n_planes);
       e.out_pl = c.G[l - 1];
       if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }
       NRW_TRY(mm(c, c.G[l], c.WT(L_SDF0 + l), M, 512, 512, e, s));
@@ -338,7 +345,8 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
     Planes DQl = dq_buf(c, l);
     NRW_TRY(mm_dw(c, c.G[l], DQl, M, L_SDF0 + l, s));
     Epi e;
-    e.aux_sig = c.A[l]; e.ld_aux = 512;
+    gate_from(c, e, l, c.gate_planes());
+    e.ld_aux = 512;
     if (l == 7) { e.aux_q = w0; e.aux_q_bcast = 1; } else { e.aux_q = c.Q[l + 1]; }
     e.out2 = c.DA2[l]; e.ld_out2 = 512;
     if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
@@ -353,7 +361,8 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
   {
     Epi e;
     e.rowvec = d_sdf; e.colvec = w0;
-    e.aux_sig = c.A[7]; e.aux_add = c.DA2[7]; e.ld_aux = 512;
+    gate_from(c, e, 7, c.gate_planes());
+    e.aux_add = c.DA2[7]; e.ld_aux = 512;
     e.out_pl = c.DA[1];
     e.colsum = c.db(L_SDF0 + 7);
     NRW_TRY(mm(c, c.DFEAT, c.WT(L_SDF8F), M, 512, 512, e, s));
@@ -362,7 +371,8 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
     Planes cur = c.DA[l & 1];
     NRW_TRY(mm_dw(c, cur, c.U[l], M, L_SDF0 + l, s));
     Epi e;
-    e.aux_sig = c.A[l - 1]; e.aux_add = c.DA2[l - 1]; e.ld_aux = 512;
+    gate_from(c, e, l - 1, c.gate_planes());
+    e.aux_add = c.DA2[l - 1]; e.ld_aux = 512;
     e.out_pl = c.DA[(l - 1) & 1];
     e.colsum = c.db(L_SDF0 + l - 1);
     if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }

@@ -11,7 +11,6 @@
 struct FwdSdfSlot {
   float* PTS;
   nrw::Planes U0, U[9], G[8], FEAT;
-  float* A[8];
   float* Q[8];
   float *c_sdf, *c_nrm;
   nrw::Planes IN1, H1, IN2, X[5];
@@ -26,6 +25,8 @@ struct nrw_ctx {
   int n_planes = 2, backend = 0, n_vocab = 0, n_a = 48;
   int bwd_planes = 0;   // 0: same as n_planes; 1: 'mixed' precision (backward GEMMs use the hi plane only)
   int cur_planes = 2;   // planes used by the GEMM helpers of the pass in flight
+  int bwd_gate_planes = 0;   // planes of u read for the softplus gates of the BACKWARD sweeps (0 = all forward planes)
+  int gate_planes() const { return bwd_gate_planes > 0 ? bwd_gate_planes : n_planes; }
   std::vector<FwdSdfSlot> sdf_slots;
   std::vector<FwdNerfSlot> nerf_slots;
   int n_slots_sdf = 1, n_slots_nerf = 1;
@@ -35,7 +36,7 @@ struct nrw_ctx {
     const FwdSdfSlot& s = sdf_slots[i];
     PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm;
     for (int l = 0; l < 9; ++l) U[l] = s.U[l];
-    for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; A[l] = s.A[l]; Q[l] = s.Q[l]; }
+    for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; Q[l] = s.Q[l]; }
     IN1 = s.IN1; H1 = s.H1; IN2 = s.IN2; c_rgb = s.c_rgb;
     for (int l = 0; l < 5; ++l) X[l] = s.X[l];
   }
@@ -58,7 +59,6 @@ struct nrw_ctx {
   // ---- chunk workspace (rows = Mc) ----
   float* PTS = nullptr;
   nrw::Planes U0, U[9], G[8], FEAT;
-  float* A[8] = {nullptr};
   float* Q[8] = {nullptr};   // Q[0] is [Mc,64]
   float* c_sdf = nullptr;
   float* c_nrm = nullptr;

@@ -3,8 +3,8 @@
 // For an accumulator element acc(m,n) of D = A * B^T the epilogue computes, in this order,
 //   v  = acc [+ bias[n]] [+ rowvec[m]*colvec[n]]
 //   out_pre[m,n] = v                                   (optional fp32 store, all N columns)
-//   w  = aux_sig ? v * softplus100'(aux_sig[m,n]) : act(v)
-//   out2[m,n] = scale * v * aux_q[m,n] * softplus100''(aux_sig[m,n])   (optional)
+//   w  = gate ? v * softplus100'(a[m,n]) : act(v)        gate: aux_sig (fp32 a) or aux_u (planes of softplus100(a))
+//   out2[m,n] = scale * v * aux_q[m,n] * softplus100''(a[m,n])   (optional)
 //   w  = aux_relu ? (aux_relu[m,n] > 0 ? w : 0) : w
 //   w  = w * scale [+ aux_add[m,n]]
 //   out_f32[m,n] (=|+=) w ; planes(out_pl)[m,n] = split_bf16(w)       (columns < n_store)
@@ -23,7 +23,10 @@ struct Epi {
   const float* bias = nullptr;
   const float* rowvec = nullptr;
   const float* colvec = nullptr;
-  const float* aux_sig = nullptr;
+  const float* aux_sig = nullptr;   // fp32 pre-activation a (legacy / test hook) ...
+  Planes aux_u = {nullptr, 0, 0};   // ... or the bf16 planes of u = softplus100(a) / aux_u_scale that the forward pass kept
+  int aux_u_planes = 0;             //     (planes to read: forward plane count, or 1 for a cheaper backward gate)
+  float aux_u_scale = 1.0f;         //     u = aux_u_scale * sum(planes)   (sqrt(2) for the skip layer's input)
   const float* aux_q = nullptr;
   const float* aux_add = nullptr;
   int aux_q_bcast = 0;  // aux_q is a [N] row vector broadcast over rows
@@ -128,18 +131,15 @@ __device__ __forceinline__ void epi_bias(const Epi& e, int m, int n0, int n_all,
 template <int NC>
 __device__ __forceinline__ void epi_math(const Epi& e, const float (&acc)[NC], const float (&a)[NC], float (&q)[NC],
                                          const float (&ad)[NC], uint32_t pos, float (&w)[NC]) {
-  if (e.aux_sig) {
-    if (e.out2) {
+  if (e.aux_sig || e.aux_u.p) {
+    const bool from_u = e.aux_u.p != nullptr;      // a[] holds u = softplus100(pre-activation) instead of the pre-activation
 #pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        float s1, s2;
-        softplus100_d12(a[j], s1, s2);
-        w[j] = acc[j] * s1 * e.scale;
-        q[j] = e.scale * acc[j] * q[j] * s2;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC; ++j) w[j] = acc[j] * softplus100_d1(a[j]) * e.scale;
+    for (int j = 0; j < NC; ++j) {
+      float s1, s2;
+      if (from_u) softplus100_d12_from_u(a[j], s1, s2);
+      else softplus100_d12(a[j], s1, s2);
+      w[j] = acc[j] * s1 * e.scale;
+      if (e.out2) q[j] = e.scale * acc[j] * q[j] * s2;
     }
   } else {
     switch (e.act) {
@@ -191,6 +191,11 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n0, float (&a
 #pragma unroll
   for (int j = 0; j < NC; ++j) a[j] = q[j] = ad[j] = 0.0f;
   if (e.aux_sig) load_f32<NC>(e.aux_sig + (long long)m * e.ld_aux + n0, n_st, a);
+  if (e.aux_u.p) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < n_st) a[j] = e.aux_u_scale * planes_load(e.aux_u, e.aux_u_planes, (long long)m * e.aux_u.ld + n0 + j);
+  }
   if (e.out2) {
     if (e.aux_q_bcast) load_f32<NC>(e.aux_q + n0, n_st, q);
     else load_f32<NC>(e.aux_q + (long long)m * e.ld_aux + n0, n_st, q);

@@ -86,6 +86,39 @@ __device__ __forceinline__ void line_store_bf16(const LineLayout& L, bf16* __res
     }
   }
 }
+// o[4*it + k] = scale * sum over planes of P[row it*8+r0][col 4*sl+k]   (tile origin: row m0w, column nc of P)
+__device__ __forceinline__ void line_load_planes(const LineLayout& L, const Planes& P, int n_planes, long long m0w, int nc, int ncols,
+                                                 float scale, float (&o)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.0f;
+  for (int pl = 0; pl < n_planes; ++pl) {
+    const bf16* src = P.plane(pl) + m0w * P.ld + nc;
+    if (L.full && ncols >= 16 && aligned8(src) && (P.ld & 3) == 0) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + (long long)(it * 8 + L.r0) * P.ld + L.sl * 4));
+        o[4 * it] += __uint_as_float(t.x << 16);
+        o[4 * it + 1] += __uint_as_float(t.x & 0xFFFF0000u);
+        o[4 * it + 2] += __uint_as_float(t.y << 16);
+        o[4 * it + 3] += __uint_as_float(t.y & 0xFFFF0000u);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + L.r0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = L.sl * 4 + k;
+          if (rr < L.rows_valid && c < ncols) o[4 * it + k] += __bfloat162float(src[(long long)rr * P.ld + c]);
+        }
+      }
+    }
+  }
+  if (scale != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] *= scale;
+  }
+}
 // bit e (= 4*it + k) set <=> src[row it*8+r0][col 4*sl+k] > 0
 __device__ __forceinline__ uint32_t line_load_posmask(const LineLayout& L, const bf16* __restrict__ src, long long ld, int ncols) {
   uint32_t pos = 0;
@@ -180,9 +213,11 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
   }
   // ---- activation / gating (elementwise, see epilogue.cuh) ----
   float w[16];
-  if (e.aux_sig) {
+  if (e.aux_sig || e.aux_u.p) {
     float a[16];
-    line_load_f32(L, e.aux_sig + (long long)m0w * e.ld_aux + nc, e.ld_aux, n_st, a);
+    const bool from_u = e.aux_u.p != nullptr;     // gate from the stored softplus OUTPUT planes (no fp32 pre-activation in HBM)
+    if (from_u) line_load_planes(L, e.aux_u, e.aux_u_planes, m0w, nc, n_st, e.aux_u_scale, a);
+    else line_load_f32(L, e.aux_sig + (long long)m0w * e.ld_aux + nc, e.ld_aux, n_st, a);
     if (e.out2) {
       float q[16];
       if (e.aux_q_bcast) {
@@ -196,14 +231,20 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float s1, s2;
-        softplus100_d12(a[i], s1, s2);
+        if (from_u) softplus100_d12_from_u(a[i], s1, s2);
+        else softplus100_d12(a[i], s1, s2);
         w[i] = x[i] * s1 * e.scale;
         q[i] = e.scale * x[i] * q[i] * s2;
       }
       line_store_f32(L, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, n_st, q, false);
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = x[i] * softplus100_d1(a[i]) * e.scale;
+      for (int i = 0; i < 16; ++i) {
+        float s1, s2;
+        if (from_u) softplus100_d12_from_u(a[i], s1, s2);
+        else softplus100_d12(a[i], s1, s2);
+        w[i] = x[i] * s1 * e.scale;
+      }
     }
   } else {
     switch (e.act) {

@@ -792,13 +792,13 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   L.mma_flops = L.flops * n_products(g.n_planes);
   L.M = g.M; L.N = g.N; L.K = g.K; L.P = g.n_planes; L.mn = g.mn_major; L.ks = g.k_slices;
   const Epi& e = g.epi;
-  L.epi = (e.out_pre ? 1u : 0u) | (e.out_f32 ? 2u : 0u) | (e.out2 ? 4u : 0u) | (e.n_planes ? 8u : 0u) | (e.aux_sig ? 16u : 0u) |
+  L.epi = (e.out_pre ? 1u : 0u) | (e.out_f32 ? 2u : 0u) | (e.out2 ? 4u : 0u) | (e.n_planes ? 8u : 0u) | ((e.aux_sig || e.aux_u.p) ? 16u : 0u) |
           ((e.aux_q && !e.aux_q_bcast) ? 32u : 0u) | (e.aux_add ? 64u : 0u) | (e.aux_relu ? 128u : 0u) | (e.atomic ? 256u : 0u) |
           (e.colsum ? 512u : 0u);
   const double mn = (double)g.M * (double)std::min(g.N, e.n_store);
   L.bytes = 2.0 * g.n_planes * ((double)g.M * g.K + (double)g.N * g.K) + (e.out_pre ? 4.0 * g.M * g.N : 0.0) +
             mn * (4.0 * ((e.out_f32 ? 1 : 0) + (e.out2 ? 1 : 0) + (e.aux_sig ? 1 : 0) + ((e.aux_q && !e.aux_q_bcast) ? 1 : 0) +
-                         (e.aux_add ? 1 : 0)) + 2.0 * e.n_planes + (e.aux_relu ? 2.0 : 0.0));
+                         (e.aux_add ? 1 : 0)) + 2.0 * e.n_planes + (e.aux_relu ? 2.0 : 0.0) + (e.aux_u.p ? 2.0 * e.aux_u_planes : 0.0));
   NRW_CUDA_OK(cudaEventRecord(L.e0, stream));
   const int rc = gemm_tc_impl(g, stream);
   NRW_CUDA_OK(cudaEventRecord(L.e1, stream));

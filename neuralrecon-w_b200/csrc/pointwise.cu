@@ -31,27 +31,50 @@ int launch_points(const float* o, const float* d, const float* z, const float* s
   return NRW_OK;
 }
 
-// ---- SDF head: sdf = softplus(a7) . w0 + b0 ; optional gbar7 = softplus'(a7) * w0 ------------------
-__global__ void __launch_bounds__(256) sdf_head_kernel(const float* __restrict__ A7, int M,
-                                                       const float* __restrict__ w0,
+// ---- SDF head: sdf = u8 . w0 + b0 with u8 = softplus(a7) read from its planes; optional gbar7 = softplus'(a7) * w0 ----
+// warp per row, lane j handles columns 4j..4j+3 of each 128-column group: 8-byte plane loads / stores
+__global__ void __launch_bounds__(256) sdf_head_kernel(Planes U8, int M, const float* __restrict__ w0,
                                                        const float* __restrict__ b0, float* __restrict__ sdf,
                                                        int n_planes, Planes G7) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= M) return;
-  const float* a = A7 + (long long)warp * 512;
+  const long long row = (long long)warp * U8.ld;
   float acc = 0.0f;
-  for (int j = lane; j < 512; j += 32) {
-    const float v = a[j], w = w0[j];
-    acc = fmaf(softplus100(v), w, acc);
-    if (G7.p) planes_store(G7, n_planes, (long long)warp * G7.ld + j, softplus100_d1(v) * w);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int j = g * 128 + lane * 4;
+    float u[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int pl = 0; pl < n_planes; ++pl) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(U8.plane(pl) + row + j));
+      u[0] += __uint_as_float(t.x << 16); u[1] += __uint_as_float(t.x & 0xFFFF0000u);
+      u[2] += __uint_as_float(t.y << 16); u[3] += __uint_as_float(t.y & 0xFFFF0000u);
+    }
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w0 + j));
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+    float gq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc = fmaf(u[k], wv[k], acc);
+      float s1, s2;
+      softplus100_d12_from_u(u[k], s1, s2);
+      gq[k] = s1 * wv[k];
+    }
+    if (G7.p) {
+      const long long grow = (long long)warp * G7.ld + j;
+      for (int pl = 0; pl < n_planes; ++pl) {
+        uint32_t pk[2];
+        split_plane<4>(gq, pk);
+        *reinterpret_cast<uint2*>(G7.plane(pl) + grow) = make_uint2(pk[0], pk[1]);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) sdf[warp] = acc + b0[0];
 }
-int launch_sdf_head(const float* A7, int M, const float* w0, const float* b0, float* sdf, int n_planes,
-                    Planes G7, cudaStream_t s) {
-  sdf_head_kernel<<<cdiv((long long)M * 32, 256), 256, 0, s>>>(A7, M, w0, b0, sdf, n_planes, G7);
+int launch_sdf_head(Planes U8, int M, const float* w0, const float* b0, float* sdf, int n_planes, Planes G7, cudaStream_t s) {
+  NRW_CHECK(U8.ld == 512 && (G7.p == nullptr || G7.ld == 512) && (U8.pstride & 3) == 0, NRW_ERR_ARG, "sdf_head: 512-wide planes expected");
+  sdf_head_kernel<<<cdiv((long long)M * 32, 256), 256, 0, s>>>(U8, M, w0, b0, sdf, n_planes, G7);
   NRW_LAUNCH_OK();
   return NRW_OK;
 }

@@ -69,6 +69,7 @@ def lib():
     L.nrw_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
     L.nrw_ctx_destroy.argtypes = [vp]
     L.nrw_ctx_set_backward_planes.argtypes = [vp, i32]
+    L.nrw_ctx_set_backward_gate_planes.argtypes = [vp, i32]
     L.nrw_packed_bytes.restype = ll
     L.nrw_packed_bytes.argtypes = [vp]
     L.nrw_workspace_bytes.restype = ll
@@ -118,7 +119,7 @@ EXPORTS = ["nrw_last_error", "nrw_version", "nrw_param_count", "nrw_param_table"
            "nrw_gemm_test_scratch_bytes", "nrw_gemm_test", "nrw_launch_count", "nrw_debug_gemm_profile",
            "nrw_gemm_timing", "nrw_ctx_set_backward_planes", "nrw_octree_build_scratch_bytes", "nrw_octree_build",
            "nrw_grad_sumsq", "nrw_adam_clip_step", "nrw_boundary_samples", "nrw_compact_scratch_bytes", "nrw_raycache_gather",
-           "nrw_grid_points_dense", "nrw_grid_points_sparse", "nrw_threshold_compact"]
+           "nrw_grid_points_dense", "nrw_grid_points_sparse", "nrw_threshold_compact", "nrw_ctx_set_backward_gate_planes"]
 
 
 def check(status, what=""):

@@ -46,6 +46,9 @@ class Engine:
               "nrw_ctx_create")
         if self.bwd_planes:
             check(self.L.nrw_ctx_set_backward_planes(self.ctx, self.bwd_planes), "nrw_ctx_set_backward_planes")
+        gate = int(os.environ.get("NRW_BWD_GATE_PLANES", 0))
+        if gate:
+            check(self.L.nrw_ctx_set_backward_gate_planes(self.ctx, min(gate, self.n_planes)), "nrw_ctx_set_backward_gate_planes")
         self.flat = None
         self.packed = None
         self.workspace = None
