@@ -1,0 +1,227 @@
+// Compile-time specialised epilogues of the CTA-pair tcgen05 GEMM for the seven layer kinds that make up > 95 % of a
+// training step.  Same arithmetic, in the same order, as the runtime-parameterised epi_chunk16 (epilogue_tc.cuh) - the
+// difference is what is NOT executed: ncu's source view of the generic epilogue showed ISETP + BRA + LOP3 + IMAD + LDC
+// (flag tests, alignment checks, 64-bit address arithmetic, ReLU bit masks) at > 50 % of all issued instructions and
+// the useful FADD / FMUL / F2FP at ~12 % (profiles/r2_gemm_epilogue_opmix.txt), with the backward layers of the
+// `mixed` mode (one MMA product) bound by epilogue instruction issue, not by the tensor pipe or HBM.
+//
+// A kind is chosen on the host (pick_epi_kind) from the Epi descriptor; anything that does not match exactly, ragged
+// edge tiles and the column boundary of the skip layer (n_store = 473) fall back to epi_chunk16, warp-uniformly.
+#pragma once
+#include "epilogue_tc.cuh"
+
+namespace nrw {
+
+enum EpiKind {
+  EK_GENERIC = 0,
+  EK_FWD_SOFTPLUS,   // x + bias -> softplus100 -> * scale -> planes                              (SDF forward layers)
+  EK_FWD_RELU,       // x + bias -> relu -> planes                                                 (colour / NeRF forward)
+  EK_FWD_NONE,       // x + bias -> planes                                                         (feature layers)
+  EK_GATE_FWD,       // out_pre = x ; w = x * softplus'(a) * scale -> planes                       (gradient chain, forward)
+  EK_TANGENT,        // w = x * s1 * scale ; out2 = scale * x * q * s2 ; w -> planes | out_f32     (tangent sweep)
+  EK_REVERSE,        // [x += rv * cv] ; w = x * s1 * scale + aux_add -> planes (+ column sums)    (reverse sweep)
+  EK_RELU_BWD,       // [x += rv * cv] ; w = relu'(fwd) ? x * scale : 0 -> planes (+ column sums)  (ReLU nets, backward)
+  EK_COUNT
+};
+
+// host: which specialisation implements `e` exactly (pointers 16-byte aligned, leading dimensions % 4 == 0 assumed by the
+// fast paths are verified here once per launch instead of once per chunk)
+inline int pick_epi_kind(const Epi& e) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (e.atomic || e.aux_sig || e.n_planes > 3) return EK_GENERIC;
+  if (e.n_planes > 0 && (!al16(e.out_pl.p) || (e.out_pl.ld & 3) || (e.out_pl.pstride & 7))) return EK_GENERIC;
+  if (e.aux_u.p && (!al16(e.aux_u.p) || (e.aux_u.ld & 3) || (e.aux_u.pstride & 7))) return EK_GENERIC;
+  if ((e.out_pre && (!al16(e.out_pre) || (e.ld_pre & 3))) || (e.out_f32 && (!al16(e.out_f32) || (e.ld_f32 & 3))) ||
+      (e.out2 && (!al16(e.out2) || (e.ld_out2 & 3))) || ((e.aux_add || (e.aux_q && !e.aux_q_bcast)) && (e.ld_aux & 3)) ||
+      (e.aux_add && !al16(e.aux_add)) || (e.aux_q && !al16(e.aux_q)) || (e.aux_relu && (!al16(e.aux_relu) || (e.ld_relu & 3))) ||
+      (e.bias && !al16(e.bias)) || (e.colvec && !al16(e.colvec)))
+    return EK_GENERIC;
+  const bool gate = e.aux_u.p != nullptr;
+  if (gate && e.out_pre && !e.out2 && !e.aux_add && !e.colsum && !e.bias && !e.rowvec && !e.aux_relu && e.n_planes > 0 && !e.out_f32)
+    return EK_GATE_FWD;
+  if (gate && e.out2 && e.aux_q && !e.out_pre && !e.bias && !e.rowvec && !e.aux_add && !e.colsum && !e.aux_relu &&
+      ((e.n_planes > 0) != (e.out_f32 != nullptr)))
+    return EK_TANGENT;
+  if (gate && e.aux_add && !e.out2 && !e.out_pre && !e.bias && !e.aux_relu && e.n_planes > 0 && !e.out_f32) return EK_REVERSE;
+  if (!gate && e.aux_relu && !e.out_pre && !e.out2 && !e.aux_add && !e.bias && e.n_planes > 0 && !e.out_f32 && e.act == ACT_NONE)
+    return EK_RELU_BWD;
+  if (!gate && e.bias && !e.rowvec && !e.aux_relu && !e.aux_add && !e.out_pre && !e.out2 && !e.out_f32 && !e.colsum && e.n_planes > 0) {
+    if (e.act == ACT_SOFTPLUS100) return EK_FWD_SOFTPLUS;
+    if (e.act == ACT_RELU) return EK_FWD_RELU;
+    if (e.act == ACT_NONE) return EK_FWD_NONE;
+  }
+  return EK_GENERIC;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void unpack_bf16x4(const uint2 t, float (&o)[4]) {
+  o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xFFFF0000u);
+  o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xFFFF0000u);
+}
+
+template <int EK>
+__device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
+                                           float* cs_tile) {
+  if constexpr (EK == EK_GENERIC) {
+    epi_chunk16(e, stg, v, m0w, nc, M, N, lane, cs_tile);
+    return;
+  } else {
+    // ragged edge tile / column boundary of the stored range: the generic path handles every case
+    if (M - m0w < 32 || N - nc < 16 || e.n_store - nc < 16) {
+      epi_chunk16(e, stg, v, m0w, nc, M, N, lane, cs_tile);
+      return;
+    }
+    const int sl = lane & 3, r0 = lane >> 2;
+    // ---- the one transpose: row layout -> line layout (identical to epi_chunk16) ----
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      *reinterpret_cast<float4*>(stg + lane * 16 + ((s ^ ((lane >> 1) & 3)) << 2)) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+    __syncwarp();
+    float x[16];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + r0;
+      const float4 t = *reinterpret_cast<const float4*>(stg + rr * 16 + ((sl ^ ((rr >> 1) & 3)) << 2));
+      x[4 * it] = t.x; x[4 * it + 1] = t.y; x[4 * it + 2] = t.z; x[4 * it + 3] = t.w;
+    }
+    __syncwarp();
+    const int col = nc + sl * 4;                      // this lane's 4 columns
+    const long long row = (long long)m0w + r0;        // this lane's first row; rows row + 8*it
+    float w[16];
+
+    if constexpr (EK == EK_FWD_SOFTPLUS || EK == EK_FWD_RELU || EK == EK_FWD_NONE) {
+      const float4 b = ldg4(e.bias + col);
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float t = x[i] + bb[i & 3];
+        if constexpr (EK == EK_FWD_SOFTPLUS) w[i] = softplus100(t) * e.scale;
+        else if constexpr (EK == EK_FWD_RELU) w[i] = fmaxf(t, 0.0f) * e.scale;
+        else w[i] = t * e.scale;
+      }
+    }
+    if constexpr (EK == EK_REVERSE || EK == EK_RELU_BWD) {
+      if (e.rowvec) {
+        const float4 c = ldg4(e.colvec + col);
+        const float cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float rv = __ldg(e.rowvec + row + it * 8);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x[4 * it + k] = fmaf(rv, cc[k], x[4 * it + k]);
+        }
+      }
+    }
+    if constexpr (EK == EK_GATE_FWD) {
+      float* op = e.out_pre + row * e.ld_pre + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        *reinterpret_cast<float4*>(op + (long long)it * 8 * e.ld_pre) = make_float4(x[4 * it], x[4 * it + 1], x[4 * it + 2], x[4 * it + 3]);
+    }
+    if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
+      // u = aux_u_scale * sum(planes of softplus output); gates from u (common.cuh)
+      float u[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) u[i] = 0.0f;
+      for (int pl = 0; pl < e.aux_u_planes; ++pl) {
+        const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float t4[4];
+          unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld)), t4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
+        }
+      }
+      const float us = e.aux_u_scale;
+      if constexpr (EK == EK_TANGENT) {
+        float q[16];
+        if (e.aux_q_bcast) {
+          const float4 qb = ldg4(e.aux_q + col);
+          const float qq[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = qq[i & 3];
+        } else {
+          const float* qp = e.aux_q + row * e.ld_aux + col;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const float4 t = ldg4(qp + (long long)it * 8 * e.ld_aux);
+            q[4 * it] = t.x; q[4 * it + 1] = t.y; q[4 * it + 2] = t.z; q[4 * it + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float s1, s2;
+          softplus100_d12_from_u(u[i] * us, s1, s2);
+          w[i] = x[i] * s1 * e.scale;
+          q[i] = e.scale * x[i] * q[i] * s2;
+        }
+        float* o2 = e.out2 + row * e.ld_out2 + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          *reinterpret_cast<float4*>(o2 + (long long)it * 8 * e.ld_out2) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float s1, s2;
+          softplus100_d12_from_u(u[i] * us, s1, s2);
+          w[i] = x[i] * s1 * e.scale;
+        }
+      }
+      if constexpr (EK == EK_REVERSE) {
+        const float* ap = e.aux_add + row * e.ld_aux + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 t = ldg4(ap + (long long)it * 8 * e.ld_aux);
+          w[4 * it] += t.x; w[4 * it + 1] += t.y; w[4 * it + 2] += t.z; w[4 * it + 3] += t.w;
+        }
+      }
+    }
+    if constexpr (EK == EK_RELU_BWD) {
+      const bf16* rp = e.aux_relu + row * e.ld_relu + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        float f[4];
+        unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(rp + (long long)it * 8 * e.ld_relu)), f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[4 * it + k] = f[k] > 0.0f ? x[4 * it + k] * e.scale : 0.0f;
+      }
+    }
+    if constexpr (EK == EK_REVERSE || EK == EK_RELU_BWD) {
+      if (e.colsum) {
+        // column sums over the 32 rows: 4 rows per lane, then the 8 lanes sharing a column slot
+        float cs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cs[k] = (w[k] + w[4 + k]) + (w[8 + k] + w[12 + k]);
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(0xFFFFFFFFu, cs[k], o);
+        }
+        if (lane < 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (cs_tile) atomicAdd(cs_tile + lane * 4 + k, cs[k]);
+            else atomicAdd(e.colsum + nc + lane * 4 + k, cs[k]);
+          }
+        }
+      }
+    }
+    if constexpr (EK == EK_TANGENT) {
+      if (e.out_f32) {
+        float* of = e.out_f32 + row * e.ld_f32 + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          *reinterpret_cast<float4*>(of + (long long)it * 8 * e.ld_f32) = make_float4(w[4 * it], w[4 * it + 1], w[4 * it + 2], w[4 * it + 3]);
+      }
+    }
+    for (int pl = 0; pl < e.n_planes; ++pl) {
+      uint32_t pk[8];
+      split_plane<16>(w, pk);
+      bf16* dp = e.out_pl.plane(pl) + row * e.out_pl.ld + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) *reinterpret_cast<uint2*>(dp + (long long)it * 8 * e.out_pl.ld) = make_uint2(pk[2 * it], pk[2 * it + 1]);
+    }
+  }
+}
+
+}  // namespace nrw

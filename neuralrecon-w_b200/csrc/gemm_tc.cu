@@ -23,7 +23,7 @@
 #include <stdio.h>
 
 #include "gemm.h"
-#include "epilogue_tc.cuh"
+#include "epilogue_fast.cuh"
 
 namespace nrw {
 
@@ -432,7 +432,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
 
-template <int MN_MAJOR>
+template <int MN_MAJOR, int EK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   constexpr int A_TILE = BM * BK * 2;              // this CTA's 128 rows of A
   constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
@@ -632,7 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
           if (nc >= p.N) break;
           float v[16];
           tmem_ld16(tmem_base + acc * BN2 + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
-          if (!(p.dbg & 1)) epi_chunk16(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
+          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
         }
       }
       tc_fence_before();
@@ -749,6 +749,17 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   return NRW_OK;
 }
 
+template <int MN, int EK>
+static int launch2(const TcParams& p, int pairs, int dev, cudaStream_t stream) {
+  static bool attr_set[MAX_DEV] = {false};
+  if (!attr_set[dev]) {
+    NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  gemm_tc2_kernel<MN, EK><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
+  return NRW_OK;
+}
+
 static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream);
 
 // ---- live kernel timing (bench.py roofline): CUDA events around every launch on the launching stream ----
@@ -842,17 +853,24 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         NRW_TRY(make_map(&p.tmB[pl], g.B.plane(pl), g.N, g.K, g.B.ld, 64, BK));
       }
     }
-    static bool attr2[MAX_DEV][2] = {{false, false}};
-    if (!attr2[dev][g.mn_major ? 1 : 0]) {
-      if (g.mn_major) NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      else NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr2[dev][g.mn_major ? 1 : 0] = true;
-    }
     const int items = p.m_tiles * p.n_tiles * p.k_slices;
     int pairs = n_sm / 2;
     if (items < pairs) pairs = items;
-    if (g.mn_major) gemm_tc2_kernel<1><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
-    else gemm_tc2_kernel<0><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
+    static const int use_fast = getenv("NRW_EPI_FAST") ? atoi(getenv("NRW_EPI_FAST")) : 1;   // 0: generic epilogue everywhere
+    const int ek = (g.mn_major || !use_fast) ? EK_GENERIC : pick_epi_kind(g.epi);
+    if (g.mn_major) { NRW_TRY((launch2<1, EK_GENERIC>(p, pairs, dev, stream))); }
+    else {
+      switch (ek) {
+        case EK_FWD_SOFTPLUS: NRW_TRY((launch2<0, EK_FWD_SOFTPLUS>(p, pairs, dev, stream))); break;
+        case EK_FWD_RELU: NRW_TRY((launch2<0, EK_FWD_RELU>(p, pairs, dev, stream))); break;
+        case EK_FWD_NONE: NRW_TRY((launch2<0, EK_FWD_NONE>(p, pairs, dev, stream))); break;
+        case EK_GATE_FWD: NRW_TRY((launch2<0, EK_GATE_FWD>(p, pairs, dev, stream))); break;
+        case EK_TANGENT: NRW_TRY((launch2<0, EK_TANGENT>(p, pairs, dev, stream))); break;
+        case EK_REVERSE: NRW_TRY((launch2<0, EK_REVERSE>(p, pairs, dev, stream))); break;
+        case EK_RELU_BWD: NRW_TRY((launch2<0, EK_RELU_BWD>(p, pairs, dev, stream))); break;
+        default: NRW_TRY((launch2<0, EK_GENERIC>(p, pairs, dev, stream)));
+      }
+    }
     NRW_LAUNCH_OK();
     ++g_tc_launches;
     return NRW_OK;
