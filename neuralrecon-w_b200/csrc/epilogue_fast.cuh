@@ -59,6 +59,36 @@ __device__ __forceinline__ void unpack_bf16x4(const uint2 t, float (&o)[4]) {
   o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xFFFF0000u);
 }
 
+// softplus gates from the stored softplus OUTPUT, 3 instructions: e = 2^(-100 log2(e) u) = 1 - sigmoid(100 a); s1 = 1 - e.
+// (No small-argument series and no threshold select as in softplus100_d12_from_u: the absolute error of s1 is <= 1 ulp of
+//  1.0 = 6e-8 and s2 = 100 s1 e is 2e-7 instead of exactly 0 above the softplus threshold - both far below the
+//  accumulation error of the GEMM that produced the value the gate multiplies.)
+#define NRW_GATE_K (-144.269504088896341f)   // -100 * log2(e)
+
+// column sums of a 32 x 16 line-layout tile (w[4*it + k] = row it*8 + (lane>>2), column 4*(lane&3) + k) into cs[16]:
+// rows first (registers), then a halving butterfly over the 8 lanes that share a column slot: 4 SHFL instead of 12
+__device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, float* cs_tile, float* cs_global) {
+  float c0 = (w[0] + w[4]) + (w[8] + w[12]), c1 = (w[1] + w[5]) + (w[9] + w[13]);
+  float c2 = (w[2] + w[6]) + (w[10] + w[14]), c3 = (w[3] + w[7]) + (w[11] + w[15]);
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  // round 1 (xor 16): lanes with bit 4 clear keep columns 0,1; the others keep 2,3
+  const float s0 = hi16 ? c0 : c2, s1 = hi16 ? c1 : c3;
+  float k0 = hi16 ? c2 : c0, k1 = hi16 ? c3 : c1;
+  k0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 16);
+  k1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 16);
+  // round 2 (xor 8): bit 3 clear keeps the first of the two, set keeps the second
+  const float s = hi8 ? k0 : k1;
+  float k = hi8 ? k1 : k0;
+  k += __shfl_xor_sync(0xFFFFFFFFu, s, 8);
+  // round 3 (xor 4): both partners hold the same column
+  k += __shfl_xor_sync(0xFFFFFFFFu, k, 4);
+  if ((lane & 4) == 0) {
+    const int colk = (lane & 3) * 4 + (hi16 ? 2 : 0) + (hi8 ? 1 : 0);
+    if (cs_tile) atomicAdd(cs_tile + colk, k);
+    else atomicAdd(cs_global + colk, k);
+  }
+}
+
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
                                            float* cs_tile) {
@@ -119,11 +149,19 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
         *reinterpret_cast<float4*>(op + (long long)it * 8 * e.ld_pre) = make_float4(x[4 * it], x[4 * it + 1], x[4 * it + 2], x[4 * it + 3]);
     }
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
-      // u = aux_u_scale * sum(planes of softplus output); gates from u (common.cuh)
+      // u = sum(planes of the softplus output); e = 2^(K u) with the plane scale folded into K
       float u[16];
+      {
+        const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) u[i] = 0.0f;
-      for (int pl = 0; pl < e.aux_u_planes; ++pl) {
+        for (int it = 0; it < 4; ++it) {
+          float t4[4];
+          unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld)), t4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
+        }
+      }
+      for (int pl = 1; pl < e.aux_u_planes; ++pl) {
         const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -133,7 +171,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
           for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
         }
       }
-      const float us = e.aux_u_scale;
+      const float kk = NRW_GATE_K * e.aux_u_scale, sc = e.scale;
       if constexpr (EK == EK_TANGENT) {
         float q[16];
         if (e.aux_q_bcast) {
@@ -149,31 +187,37 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
             q[4 * it] = t.x; q[4 * it + 1] = t.y; q[4 * it + 2] = t.z; q[4 * it + 3] = t.w;
           }
         }
+        const float sc100 = 100.0f * sc;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s1, s2;
-          softplus100_d12_from_u(u[i] * us, s1, s2);
-          w[i] = x[i] * s1 * e.scale;
-          q[i] = e.scale * x[i] * q[i] * s2;
+          const float ee = mufu_ex2(u[i] * kk);
+          const float s1 = 1.0f - ee;
+          const float xs = x[i] * s1;
+          w[i] = xs * sc;                                  // x * softplus'(a) * scale
+          q[i] = (xs * q[i]) * (ee * sc100);               // scale * x * q * softplus''(a),  softplus'' = 100 s1 e
         }
         float* o2 = e.out2 + row * e.ld_out2 + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it)
           *reinterpret_cast<float4*>(o2 + (long long)it * 8 * e.ld_out2) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float s1, s2;
-          softplus100_d12_from_u(u[i] * us, s1, s2);
-          w[i] = x[i] * s1 * e.scale;
-        }
-      }
-      if constexpr (EK == EK_REVERSE) {
+      } else if constexpr (EK == EK_REVERSE) {
         const float* ap = e.aux_add + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const float4 t = ldg4(ap + (long long)it * 8 * e.ld_aux);
-          w[4 * it] += t.x; w[4 * it + 1] += t.y; w[4 * it + 2] += t.z; w[4 * it + 3] += t.w;
+          const float ad[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * it + k;
+            const float ee = mufu_ex2(u[i] * kk);
+            w[i] = fmaf(x[i], fmaf(-sc, ee, sc), ad[k]);  // x * (1 - e) * scale + aux_add
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float ee = mufu_ex2(u[i] * kk);
+          w[i] = x[i] * fmaf(-sc, ee, sc);
         }
       }
     }
@@ -188,23 +232,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_REVERSE || EK == EK_RELU_BWD) {
-      if (e.colsum) {
-        // column sums over the 32 rows: 4 rows per lane, then the 8 lanes sharing a column slot
-        float cs[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          cs[k] = (w[k] + w[4 + k]) + (w[8 + k] + w[12 + k]);
-#pragma unroll
-          for (int o = 4; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(0xFFFFFFFFu, cs[k], o);
-        }
-        if (lane < 4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (cs_tile) atomicAdd(cs_tile + lane * 4 + k, cs[k]);
-            else atomicAdd(e.colsum + nc + lane * 4 + k, cs[k]);
-          }
-        }
-      }
+      if (e.colsum) line_colsum_add(w, lane, cs_tile, e.colsum + nc);
     }
     if constexpr (EK == EK_TANGENT) {
       if (e.out_f32) {
@@ -216,7 +244,15 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     }
     for (int pl = 0; pl < e.n_planes; ++pl) {
       uint32_t pk[8];
-      split_plane<16>(w, pk);
+      if (pl + 1 < e.n_planes) {
+        split_plane<16>(w, pk);                            // rounded plane, residual stays in w
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {                      // last plane: no residual needed
+          const __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * t], w[2 * t + 1]);
+          pk[t] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
       bf16* dp = e.out_pl.plane(pl) + row * e.out_pl.ld + col;
 #pragma unroll
       for (int it = 0; it < 4; ++it) *reinterpret_cast<uint2*>(dp + (long long)it * 8 * e.out_pl.ld) = make_uint2(pk[2 * it], pk[2 * it + 1]);
