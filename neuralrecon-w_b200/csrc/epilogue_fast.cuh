@@ -89,6 +89,28 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
   }
 }
 
+// L2 prefetch of the auxiliary epilogue streams of one 128-row x 256-column tile (this CTA's half of a CTA-pair item).
+// The epilogue warps are latency-bound on these streams (16 warps x one 32 x 16 chunk in flight each ~ 48 KB per SM); a
+// bulk L2 prefetch issued one tile ahead needs no registers and turns the HBM round trip into an L2 hit.
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <int EK>
+__device__ __forceinline__ void prefetch_aux_tile(const Epi& e, int m0, int n0, int M, int N, int ew, int lane) {
+  if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE || EK == EK_RELU_BWD) {
+    const int r = m0 + ew * 8 + lane;                 // 16 epilogue warps x 8 lanes = the 128 rows of the tile
+    if (lane >= 8 || r >= M || n0 + 256 > N || n0 + 256 > e.n_store) return;
+    if constexpr (EK != EK_RELU_BWD) {
+      for (int pl = 0; pl < e.aux_u_planes; ++pl) l2_prefetch(e.aux_u.plane(pl) + (long long)r * e.aux_u.ld + n0, 512);
+    }
+    if constexpr (EK == EK_TANGENT) {
+      if (!e.aux_q_bcast) l2_prefetch(e.aux_q + (long long)r * e.ld_aux + n0, 1024);
+    }
+    if constexpr (EK == EK_REVERSE) l2_prefetch(e.aux_add + (long long)r * e.ld_aux + n0, 1024);
+    if constexpr (EK == EK_RELU_BWD) l2_prefetch(e.aux_relu + (long long)r * e.ld_relu + n0, 512);
+  }
+}
+
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
                                            float* cs_tile) {
@@ -102,6 +124,42 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       return;
     }
     const int sl = lane & 3, r0 = lane >> 2;
+    const int col = nc + sl * 4;                      // this lane's 4 columns
+    const long long row = (long long)m0w + r0;        // this lane's first row; rows row + 8*it
+    // ---- auxiliary streams first (raw registers): their latency overlaps the transpose below ----
+    uint2 ru0[4], ru1[4];
+    float4 rf[4];
+    if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
+      const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) ru0[it] = __ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld));
+      if (e.aux_u_planes > 1) {
+        const bf16* up1 = up + e.aux_u.pstride;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) ru1[it] = __ldg(reinterpret_cast<const uint2*>(up1 + (long long)it * 8 * e.aux_u.ld));
+      }
+    }
+    if constexpr (EK == EK_TANGENT) {
+      if (!e.aux_q_bcast) {
+        const float* qp = e.aux_q + row * e.ld_aux + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) rf[it] = ldg4(qp + (long long)it * 8 * e.ld_aux);
+      } else {
+        const float4 qb = ldg4(e.aux_q + col);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) rf[it] = qb;
+      }
+    }
+    if constexpr (EK == EK_REVERSE) {
+      const float* ap = e.aux_add + row * e.ld_aux + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) rf[it] = ldg4(ap + (long long)it * 8 * e.ld_aux);
+    }
+    if constexpr (EK == EK_RELU_BWD) {
+      const bf16* rp = e.aux_relu + row * e.ld_relu + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) ru0[it] = __ldg(reinterpret_cast<const uint2*>(rp + (long long)it * 8 * e.ld_relu));
+    }
     // ---- the one transpose: row layout -> line layout (identical to epi_chunk16) ----
 #pragma unroll
     for (int s = 0; s < 4; ++s)
@@ -115,8 +173,6 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       x[4 * it] = t.x; x[4 * it + 1] = t.y; x[4 * it + 2] = t.z; x[4 * it + 3] = t.w;
     }
     __syncwarp();
-    const int col = nc + sl * 4;                      // this lane's 4 columns
-    const long long row = (long long)m0w + r0;        // this lane's first row; rows row + 8*it
     float w[16];
 
     if constexpr (EK == EK_FWD_SOFTPLUS || EK == EK_FWD_RELU || EK == EK_FWD_NONE) {
@@ -151,17 +207,23 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
       // u = sum(planes of the softplus output); e = 2^(K u) with the plane scale folded into K
       float u[16];
-      {
-        const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        float t4[4];
+        unpack_bf16x4(ru0[it], t4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
+      }
+      if (e.aux_u_planes > 1) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float t4[4];
-          unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld)), t4);
+          unpack_bf16x4(ru1[it], t4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
+          for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
         }
       }
-      for (int pl = 1; pl < e.aux_u_planes; ++pl) {
+      for (int pl = 2; pl < e.aux_u_planes; ++pl) {         // third plane (bf16x6 mode): loaded in place
         const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -174,19 +236,8 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       const float kk = NRW_GATE_K * e.aux_u_scale, sc = e.scale;
       if constexpr (EK == EK_TANGENT) {
         float q[16];
-        if (e.aux_q_bcast) {
-          const float4 qb = ldg4(e.aux_q + col);
-          const float qq[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) q[i] = qq[i & 3];
-        } else {
-          const float* qp = e.aux_q + row * e.ld_aux + col;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const float4 t = ldg4(qp + (long long)it * 8 * e.ld_aux);
-            q[4 * it] = t.x; q[4 * it + 1] = t.y; q[4 * it + 2] = t.z; q[4 * it + 3] = t.w;
-          }
-        }
+        for (int it = 0; it < 4; ++it) { q[4 * it] = rf[it].x; q[4 * it + 1] = rf[it].y; q[4 * it + 2] = rf[it].z; q[4 * it + 3] = rf[it].w; }
         const float sc100 = 100.0f * sc;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -201,11 +252,9 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
         for (int it = 0; it < 4; ++it)
           *reinterpret_cast<float4*>(o2 + (long long)it * 8 * e.ld_out2) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
       } else if constexpr (EK == EK_REVERSE) {
-        const float* ap = e.aux_add + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const float4 t = ldg4(ap + (long long)it * 8 * e.ld_aux);
-          const float ad[4] = {t.x, t.y, t.z, t.w};
+          const float ad[4] = {rf[it].x, rf[it].y, rf[it].z, rf[it].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int i = 4 * it + k;
@@ -222,11 +271,10 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_RELU_BWD) {
-      const bf16* rp = e.aux_relu + row * e.ld_relu + col;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         float f[4];
-        unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(rp + (long long)it * 8 * e.ld_relu)), f);
+        unpack_bf16x4(ru0[it], f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[4 * it + k] = f[k] > 0.0f ? x[4 * it + k] * e.scale : 0.0f;
       }

@@ -607,12 +607,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
+    static_assert(N_EPI_WARPS == 16, "prefetch_aux_tile maps 16 warps x 8 lanes onto the 128 rows of a tile");
+    if (EK != EK_GENERIC && unit < n_items && p.k_slices == 1)
+      prefetch_aux_tile<EK>(p.epi, (unit / p.n_tiles) * (2 * BM) + (int)rank * BM, (unit % p.n_tiles) * BN2, p.M, p.N, ew, lane);
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
       const int n0 = (t % p.n_tiles) * BN2;
       const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+      if (EK != EK_GENERIC && p.k_slices == 1 && item + n_units < n_items) {   // aux streams of the NEXT tile -> L2
+        const int tn = item + n_units;
+        prefetch_aux_tile<EK>(p.epi, (tn / p.n_tiles) * (2 * BM) + (int)rank * BM, (tn % p.n_tiles) * BN2, p.M, p.N, ew, lane);
+      }
       if (use_cs && n0 != cs_n0) {
         if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
         cs_n0 = n0;

@@ -46,7 +46,10 @@ class Engine:
               "nrw_ctx_create")
         if self.bwd_planes:
             check(self.L.nrw_ctx_set_backward_planes(self.ctx, self.bwd_planes), "nrw_ctx_set_backward_planes")
-        gate = int(os.environ.get("NRW_BWD_GATE_PLANES", 0))
+        # backward sweeps rebuild softplus'(a) / softplus''(a) from the stored output planes: with plain-bf16 backward GEMMs
+        # ('mixed') the hi plane alone is enough (gradient cosine vs the fp32 reference 0.9999998 either way,
+        # profiles/r2_precision_study.json); the strict modes read every plane
+        gate = int(os.environ.get("NRW_BWD_GATE_PLANES", 1 if self.bwd_planes == 1 else 0))
         if gate:
             check(self.L.nrw_ctx_set_backward_gate_planes(self.ctx, min(gate, self.n_planes)), "nrw_ctx_set_backward_gate_planes")
         self.flat = None
