@@ -1,4 +1,5 @@
 // extern "C" surface of libnrw.so (include/nrw.h).  No exceptions cross this boundary.
+#include <stdlib.h>
 #include <new>
 
 #include "engine.h"
@@ -62,7 +63,12 @@ int nrw_ctx_create(nrw_ctx** out, int n_planes, int gemm_backend, int n_vocab, i
 int nrw_ctx_set_backward_planes(nrw_ctx* ctx, int n) {
   NRW_GUARD_BEGIN
   NRW_CHECK(ctx && n >= 0 && n <= ctx->n_planes, NRW_ERR_ARG, "set_backward_planes: n=%d out of range", n);
+  NRW_CHECK(!ctx->bound, NRW_ERR_STATE, "set_backward_planes: call before nrw_ctx_bind (it changes the workspace layout)");
   ctx->bwd_planes = n;
+  // plain-bf16 backward: the fp32 side streams only the backward pass reads (Q_l of the gradient chain, the second-order
+  // terms of the tangent sweep) are kept as ONE bf16 plane as well - their consumers multiply them into bf16 operands
+  const char* env = getenv("NRW_AUX_BF16");
+  ctx->aux_bf16 = n == 1 && ctx->n_planes > 1 && ctx->backend == NRW_GEMM_TCGEN05 && !(env && atoi(env) == 0);
   return NRW_OK;
   NRW_GUARD_END
 }

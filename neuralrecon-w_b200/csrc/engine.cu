@@ -43,7 +43,12 @@ static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, in
     for (int l = 1; l <= 8; ++l) s.U[l] = cv.planes(M, 512, P);
     for (int l = 0; l < 8; ++l) s.G[l] = cv.planes(M, 512, P);
     s.Q[0] = cv.f32(M * 64);
-    for (int l = 1; l < 8; ++l) s.Q[l] = cv.f32(M * 512);
+    for (int l = 1; l < 8; ++l) {
+      s.Q[l] = nullptr; s.Qh[l] = nullptr;
+      if (c.aux_bf16 && l != 4) s.Qh[l] = reinterpret_cast<bf16*>(cv.take(M * 512 * 2));
+      else s.Q[l] = cv.f32(M * 512);
+    }
+    s.Qh[0] = nullptr;
     s.FEAT = cv.planes(M, 512, P);
     s.c_sdf = cv.f32(M);
     s.c_nrm = cv.f32(M * 3);
@@ -81,7 +86,11 @@ static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, in
     c.DA[1] = cv.planes(M, 512, P);
     c.DFEAT = cv.planes(M, 512, P);
     c.DQ8f = cv.f32(M * 512);
-    for (int l = 0; l < 8; ++l) c.DA2[l] = cv.f32(M * 512);
+    for (int l = 0; l < 8; ++l) {
+      c.DA2[l] = nullptr; c.DA2h[l] = nullptr;
+      if (c.aux_bf16) c.DA2h[l] = reinterpret_cast<bf16*>(cv.take(M * 512 * 2));
+      else c.DA2[l] = cv.f32(M * 512);
+    }
     c.dX[0] = cv.planes(M, 256, P);
     c.dX[1] = cv.planes(M, 256, P);
     c.dH2 = cv.planes(M, 128, P);
@@ -212,7 +221,7 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
   if (need_normal) {
     for (int l = 7; l >= 1; --l) {
       Epi e;
-      e.out_pre = c.Q[l]; e.ld_pre = 512;
+      e.out_pre = c.Q[l]; e.out_pre_h = c.Qh[l]; e.ld_pre = 512;     // exactly one of the two is allocated
       gate_from(c, e, l - 1, c.n_planes);
       e.out_pl = c.G[l - 1];
       if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }
@@ -347,8 +356,8 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
     Epi e;
     gate_from(c, e, l, c.gate_planes());
     e.ld_aux = 512;
-    if (l == 7) { e.aux_q = w0; e.aux_q_bcast = 1; } else { e.aux_q = c.Q[l + 1]; }
-    e.out2 = c.DA2[l]; e.ld_out2 = 512;
+    if (l == 7) { e.aux_q = w0; e.aux_q_bcast = 1; } else { e.aux_q = c.Q[l + 1]; e.aux_q_h = c.Qh[l + 1]; }
+    e.out2 = c.DA2[l]; e.out2_h = c.DA2h[l]; e.ld_out2 = 512;
     if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
     if (l < 7) e.out_pl = dq_buf(c, l + 1);
     else { e.out_f32 = c.DQ8f; e.ld_f32 = 512; }
@@ -362,7 +371,7 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
     Epi e;
     e.rowvec = d_sdf; e.colvec = w0;
     gate_from(c, e, 7, c.gate_planes());
-    e.aux_add = c.DA2[7]; e.ld_aux = 512;
+    e.aux_add = c.DA2[7]; e.aux_add_h = c.DA2h[7]; e.ld_aux = 512;
     e.out_pl = c.DA[1];
     e.colsum = c.db(L_SDF0 + 7);
     NRW_TRY(mm(c, c.DFEAT, c.WT(L_SDF8F), M, 512, 512, e, s));
@@ -372,7 +381,7 @@ int sdf_chunk_backward(nrw_ctx& c, int M, const float* pts, const float* d_sdf, 
     NRW_TRY(mm_dw(c, cur, c.U[l], M, L_SDF0 + l, s));
     Epi e;
     gate_from(c, e, l - 1, c.gate_planes());
-    e.aux_add = c.DA2[l - 1]; e.ld_aux = 512;
+    e.aux_add = c.DA2[l - 1]; e.aux_add_h = c.DA2h[l - 1]; e.ld_aux = 512;
     e.out_pl = c.DA[(l - 1) & 1];
     e.colsum = c.db(L_SDF0 + l - 1);
     if (l == 4) { e.scale = INV_SQRT2; e.n_store = 473; }

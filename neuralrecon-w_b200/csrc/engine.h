@@ -12,6 +12,7 @@ struct FwdSdfSlot {
   float* PTS;
   nrw::Planes U0, U[9], G[8], FEAT;
   float* Q[8];
+  nrw::bf16* Qh[8];     // bf16 twin of Q[l] (l != 0, 4) when the context keeps backward-only side streams in bf16
   float *c_sdf, *c_nrm;
   nrw::Planes IN1, H1, IN2, X[5];
   float* c_rgb;
@@ -36,7 +37,7 @@ struct nrw_ctx {
     const FwdSdfSlot& s = sdf_slots[i];
     PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm;
     for (int l = 0; l < 9; ++l) U[l] = s.U[l];
-    for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; Q[l] = s.Q[l]; }
+    for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; Q[l] = s.Q[l]; Qh[l] = s.Qh[l]; }
     IN1 = s.IN1; H1 = s.H1; IN2 = s.IN2; c_rgb = s.c_rgb;
     for (int l = 0; l < 5; ++l) X[l] = s.X[l];
   }
@@ -60,6 +61,9 @@ struct nrw_ctx {
   float* PTS = nullptr;
   nrw::Planes U0, U[9], G[8], FEAT;
   float* Q[8] = {nullptr};   // Q[0] is [Mc,64]
+  nrw::bf16* Qh[8] = {nullptr};
+  nrw::bf16* DA2h[8] = {nullptr};
+  bool aux_bf16 = false;     // 'mixed': Q_l (l != 0, 4) and the second-order terms DA2_l are stored as one bf16 plane
   float* c_sdf = nullptr;
   float* c_nrm = nullptr;
   nrw::Planes IN1, H1, IN2, X[5];

@@ -37,6 +37,12 @@ struct Epi {
   float scale = 1.0f;
   float* out_pre = nullptr;
   int ld_pre = 0;
+  // bf16 (single rounded plane) variants of three fp32 side streams that only the BACKWARD pass of the `mixed` mode
+  // consumes - same leading dimensions as their fp32 twins (ld_pre / ld_aux / ld_out2), at most one of each pair is set:
+  bf16* out_pre_h = nullptr;        // Q_l of the gradient chain (read back as aux_q_h by the tangent sweep)
+  const bf16* aux_q_h = nullptr;
+  bf16* out2_h = nullptr;           // second-order term of the tangent sweep (read back as aux_add_h by the reverse sweep)
+  const bf16* aux_add_h = nullptr;
   float* out_f32 = nullptr;
   int ld_f32 = 0;
   int atomic = 0;

@@ -31,21 +31,23 @@ inline int pick_epi_kind(const Epi& e) {
   if (e.atomic || e.aux_sig || e.n_planes > 3) return EK_GENERIC;
   if (e.n_planes > 0 && (!al16(e.out_pl.p) || (e.out_pl.ld & 3) || (e.out_pl.pstride & 7))) return EK_GENERIC;
   if (e.aux_u.p && (!al16(e.aux_u.p) || (e.aux_u.ld & 3) || (e.aux_u.pstride & 7))) return EK_GENERIC;
-  if ((e.out_pre && (!al16(e.out_pre) || (e.ld_pre & 3))) || (e.out_f32 && (!al16(e.out_f32) || (e.ld_f32 & 3))) ||
-      (e.out2 && (!al16(e.out2) || (e.ld_out2 & 3))) || ((e.aux_add || (e.aux_q && !e.aux_q_bcast)) && (e.ld_aux & 3)) ||
-      (e.aux_add && !al16(e.aux_add)) || (e.aux_q && !al16(e.aux_q)) || (e.aux_relu && (!al16(e.aux_relu) || (e.ld_relu & 3))) ||
-      (e.bias && !al16(e.bias)) || (e.colvec && !al16(e.colvec)))
+  const bool pre = e.out_pre || e.out_pre_h, o2 = e.out2 || e.out2_h, q = e.aux_q || e.aux_q_h, add = e.aux_add || e.aux_add_h;
+  if ((e.out_pre && e.out_pre_h) || (e.out2 && e.out2_h) || (e.aux_q && e.aux_q_h) || (e.aux_add && e.aux_add_h)) return EK_GENERIC;
+  if ((pre && (!al16(e.out_pre) || !al16(e.out_pre_h) || (e.ld_pre & 3))) || (e.out_f32 && (!al16(e.out_f32) || (e.ld_f32 & 3))) ||
+      (o2 && (!al16(e.out2) || !al16(e.out2_h) || (e.ld_out2 & 3))) || ((add || (q && !e.aux_q_bcast)) && (e.ld_aux & 3)) ||
+      !al16(e.aux_add) || !al16(e.aux_add_h) || !al16(e.aux_q) || !al16(e.aux_q_h) ||
+      (e.aux_relu && (!al16(e.aux_relu) || (e.ld_relu & 3))) || (e.bias && !al16(e.bias)) || (e.colvec && !al16(e.colvec)))
     return EK_GENERIC;
   const bool gate = e.aux_u.p != nullptr;
-  if (gate && e.out_pre && !e.out2 && !e.aux_add && !e.colsum && !e.bias && !e.rowvec && !e.aux_relu && e.n_planes > 0 && !e.out_f32)
+  if (gate && pre && !o2 && !add && !e.colsum && !e.bias && !e.rowvec && !e.aux_relu && e.n_planes > 0 && !e.out_f32)
     return EK_GATE_FWD;
-  if (gate && e.out2 && e.aux_q && !e.out_pre && !e.bias && !e.rowvec && !e.aux_add && !e.colsum && !e.aux_relu &&
+  if (gate && o2 && q && !pre && !e.bias && !e.rowvec && !add && !e.colsum && !e.aux_relu &&
       ((e.n_planes > 0) != (e.out_f32 != nullptr)))
     return EK_TANGENT;
-  if (gate && e.aux_add && !e.out2 && !e.out_pre && !e.bias && !e.aux_relu && e.n_planes > 0 && !e.out_f32) return EK_REVERSE;
-  if (!gate && e.aux_relu && !e.out_pre && !e.out2 && !e.aux_add && !e.bias && e.n_planes > 0 && !e.out_f32 && e.act == ACT_NONE)
+  if (gate && add && !o2 && !pre && !e.bias && !e.aux_relu && e.n_planes > 0 && !e.out_f32) return EK_REVERSE;
+  if (!gate && e.aux_relu && !pre && !o2 && !add && !e.bias && e.n_planes > 0 && !e.out_f32 && e.act == ACT_NONE)
     return EK_RELU_BWD;
-  if (!gate && e.bias && !e.rowvec && !e.aux_relu && !e.aux_add && !e.out_pre && !e.out2 && !e.out_f32 && !e.colsum && e.n_planes > 0) {
+  if (!gate && e.bias && !e.rowvec && !e.aux_relu && !add && !pre && !o2 && !e.out_f32 && !e.colsum && e.n_planes > 0) {
     if (e.act == ACT_SOFTPLUS100) return EK_FWD_SOFTPLUS;
     if (e.act == ACT_RELU) return EK_FWD_RELU;
     if (e.act == ACT_NONE) return EK_FWD_NONE;
@@ -89,28 +91,8 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
   }
 }
 
-// L2 prefetch of the auxiliary epilogue streams of one 128-row x 256-column tile (this CTA's half of a CTA-pair item).
-// The epilogue warps are latency-bound on these streams (16 warps x one 32 x 16 chunk in flight each ~ 48 KB per SM); a
-// bulk L2 prefetch issued one tile ahead needs no registers and turns the HBM round trip into an L2 hit.
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-template <int EK>
-__device__ __forceinline__ void prefetch_aux_tile(const Epi& e, int m0, int n0, int M, int N, int ew, int lane) {
-  if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE || EK == EK_RELU_BWD) {
-    const int r = m0 + ew * 8 + lane;                 // 16 epilogue warps x 8 lanes = the 128 rows of the tile
-    if (lane >= 8 || r >= M || n0 + 256 > N || n0 + 256 > e.n_store) return;
-    if constexpr (EK != EK_RELU_BWD) {
-      for (int pl = 0; pl < e.aux_u_planes; ++pl) l2_prefetch(e.aux_u.plane(pl) + (long long)r * e.aux_u.ld + n0, 512);
-    }
-    if constexpr (EK == EK_TANGENT) {
-      if (!e.aux_q_bcast) l2_prefetch(e.aux_q + (long long)r * e.ld_aux + n0, 1024);
-    }
-    if constexpr (EK == EK_REVERSE) l2_prefetch(e.aux_add + (long long)r * e.ld_aux + n0, 1024);
-    if constexpr (EK == EK_RELU_BWD) l2_prefetch(e.aux_relu + (long long)r * e.ld_relu + n0, 512);
-  }
-}
-
+// (A bulk L2 prefetch of the next tile's auxiliary streams, cp.async.bulk.prefetch.L2 issued one tile ahead, was measured
+//  SLOWER on the same box - 102.5 vs 98.0 ms of GEMM time per step - and removed.)
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
                                            float* cs_tile) {
@@ -127,20 +109,22 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     const int col = nc + sl * 4;                      // this lane's 4 columns
     const long long row = (long long)m0w + r0;        // this lane's first row; rows row + 8*it
     // ---- auxiliary streams first (raw registers): their latency overlaps the transpose below ----
-    uint2 ru0[4], ru1[4];
-    float4 rf[4];
+    uint2 ru0[4];                     // first gate plane (further planes are loaded in place below)
+    float4 rf[4];                     // fp32 side stream (aux_q / aux_add), or its bf16 twin's raw bits in .x/.y
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
       const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
 #pragma unroll
       for (int it = 0; it < 4; ++it) ru0[it] = __ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld));
-      if (e.aux_u_planes > 1) {
-        const bf16* up1 = up + e.aux_u.pstride;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) ru1[it] = __ldg(reinterpret_cast<const uint2*>(up1 + (long long)it * 8 * e.aux_u.ld));
-      }
     }
     if constexpr (EK == EK_TANGENT) {
-      if (!e.aux_q_bcast) {
+      if (e.aux_q_h) {
+        const bf16* qp = e.aux_q_h + row * e.ld_aux + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(qp + (long long)it * 8 * e.ld_aux));
+          rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
+        }
+      } else if (!e.aux_q_bcast) {
         const float* qp = e.aux_q + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) rf[it] = ldg4(qp + (long long)it * 8 * e.ld_aux);
@@ -151,9 +135,18 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_REVERSE) {
-      const float* ap = e.aux_add + row * e.ld_aux + col;
+      if (e.aux_add_h) {
+        const bf16* ap = e.aux_add_h + row * e.ld_aux + col;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) rf[it] = ldg4(ap + (long long)it * 8 * e.ld_aux);
+        for (int it = 0; it < 4; ++it) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ap + (long long)it * 8 * e.ld_aux));
+          rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
+        }
+      } else {
+        const float* ap = e.aux_add + row * e.ld_aux + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) rf[it] = ldg4(ap + (long long)it * 8 * e.ld_aux);
+      }
     }
     if constexpr (EK == EK_RELU_BWD) {
       const bf16* rp = e.aux_relu + row * e.ld_relu + col;
@@ -199,10 +192,20 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_GATE_FWD) {
-      float* op = e.out_pre + row * e.ld_pre + col;
+      if (e.out_pre_h) {
+        bf16* op = e.out_pre_h + row * e.ld_pre + col;
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
-        *reinterpret_cast<float4*>(op + (long long)it * 8 * e.ld_pre) = make_float4(x[4 * it], x[4 * it + 1], x[4 * it + 2], x[4 * it + 3]);
+        for (int it = 0; it < 4; ++it) {
+          const __nv_bfloat162 a = __floats2bfloat162_rn(x[4 * it], x[4 * it + 1]), b = __floats2bfloat162_rn(x[4 * it + 2], x[4 * it + 3]);
+          *reinterpret_cast<uint2*>(op + (long long)it * 8 * e.ld_pre) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        }
+      } else {
+        float* op = e.out_pre + row * e.ld_pre + col;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          *reinterpret_cast<float4*>(op + (long long)it * 8 * e.ld_pre) = make_float4(x[4 * it], x[4 * it + 1], x[4 * it + 2], x[4 * it + 3]);
+      }
     }
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
       // u = sum(planes of the softplus output); e = 2^(K u) with the plane scale folded into K
@@ -214,16 +217,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
 #pragma unroll
         for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
       }
-      if (e.aux_u_planes > 1) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          float t4[4];
-          unpack_bf16x4(ru1[it], t4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
-        }
-      }
-      for (int pl = 2; pl < e.aux_u_planes; ++pl) {         // third plane (bf16x6 mode): loaded in place
+      for (int pl = 1; pl < e.aux_u_planes; ++pl) {         // further planes: loaded in place
         const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -236,8 +230,17 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       const float kk = NRW_GATE_K * e.aux_u_scale, sc = e.scale;
       if constexpr (EK == EK_TANGENT) {
         float q[16];
+        if (e.aux_q_h) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) { q[4 * it] = rf[it].x; q[4 * it + 1] = rf[it].y; q[4 * it + 2] = rf[it].z; q[4 * it + 3] = rf[it].w; }
+          for (int it = 0; it < 4; ++it) {
+            float t4[4];
+            unpack_bf16x4(make_uint2(__float_as_uint(rf[it].x), __float_as_uint(rf[it].y)), t4);
+            q[4 * it] = t4[0]; q[4 * it + 1] = t4[1]; q[4 * it + 2] = t4[2]; q[4 * it + 3] = t4[3];
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) { q[4 * it] = rf[it].x; q[4 * it + 1] = rf[it].y; q[4 * it + 2] = rf[it].z; q[4 * it + 3] = rf[it].w; }
+        }
         const float sc100 = 100.0f * sc;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -247,14 +250,25 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
           w[i] = xs * sc;                                  // x * softplus'(a) * scale
           q[i] = (xs * q[i]) * (ee * sc100);               // scale * x * q * softplus''(a),  softplus'' = 100 s1 e
         }
-        float* o2 = e.out2 + row * e.ld_out2 + col;
+        if (e.out2_h) {
+          bf16* o2 = e.out2_h + row * e.ld_out2 + col;
 #pragma unroll
-        for (int it = 0; it < 4; ++it)
-          *reinterpret_cast<float4*>(o2 + (long long)it * 8 * e.ld_out2) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
+          for (int it = 0; it < 4; ++it) {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(q[4 * it], q[4 * it + 1]), b = __floats2bfloat162_rn(q[4 * it + 2], q[4 * it + 3]);
+            *reinterpret_cast<uint2*>(o2 + (long long)it * 8 * e.ld_out2) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+          }
+        } else {
+          float* o2 = e.out2 + row * e.ld_out2 + col;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            *reinterpret_cast<float4*>(o2 + (long long)it * 8 * e.ld_out2) = make_float4(q[4 * it], q[4 * it + 1], q[4 * it + 2], q[4 * it + 3]);
+        }
       } else if constexpr (EK == EK_REVERSE) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const float ad[4] = {rf[it].x, rf[it].y, rf[it].z, rf[it].w};
+          float ad[4] = {rf[it].x, rf[it].y, rf[it].z, rf[it].w};
+          if (e.aux_add_h) unpack_bf16x4(make_uint2(__float_as_uint(rf[it].x), __float_as_uint(rf[it].y)), ad);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int i = 4 * it + k;

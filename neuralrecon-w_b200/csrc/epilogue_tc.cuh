@@ -202,6 +202,15 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
     }
   }
   if (e.out_pre) line_store_f32(L, e.out_pre + (long long)m0w * e.ld_pre + nc, e.ld_pre, n_all, x, false);
+  if (e.out_pre_h) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * t], x[2 * t + 1]);
+      pk[t] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    line_store_bf16(L, e.out_pre_h + (long long)m0w * e.ld_pre + nc, e.ld_pre, n_all, pk);
+  }
   if (n_st <= 0) return;
   if (e.atomic) {
     if (e.scale != 1.0f) {
@@ -218,9 +227,11 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
     const bool from_u = e.aux_u.p != nullptr;     // gate from the stored softplus OUTPUT planes (no fp32 pre-activation in HBM)
     if (from_u) line_load_planes(L, e.aux_u, e.aux_u_planes, m0w, nc, n_st, e.aux_u_scale, a);
     else line_load_f32(L, e.aux_sig + (long long)m0w * e.ld_aux + nc, e.ld_aux, n_st, a);
-    if (e.out2) {
+    if (e.out2 || e.out2_h) {
       float q[16];
-      if (e.aux_q_bcast) {
+      if (e.aux_q_h) {
+        line_load_planes(L, Planes{const_cast<bf16*>(e.aux_q_h), 0, e.ld_aux}, 1, m0w, nc, n_st, 1.0f, q);
+      } else if (e.aux_q_bcast) {
         float qb[4];
         line_load_cols(L, e.aux_q + nc, n_st, qb);
 #pragma unroll
@@ -236,7 +247,17 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
         w[i] = x[i] * s1 * e.scale;
         q[i] = e.scale * x[i] * q[i] * s2;
       }
-      line_store_f32(L, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, n_st, q, false);
+      if (e.out2_h) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(q[2 * t], q[2 * t + 1]);
+          pk[t] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        line_store_bf16(L, e.out2_h + (long long)m0w * e.ld_out2 + nc, e.ld_out2, n_st, pk);
+      } else {
+        line_store_f32(L, e.out2 + (long long)m0w * e.ld_out2 + nc, e.ld_out2, n_st, q, false);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -271,9 +292,10 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, float* stg, const floa
         if (!((pos >> i) & 1u)) w[i] = 0.0f;
     }
   }
-  if (e.aux_add) {
+  if (e.aux_add || e.aux_add_h) {
     float ad[16];
-    line_load_f32(L, e.aux_add + (long long)m0w * e.ld_aux + nc, e.ld_aux, n_st, ad);
+    if (e.aux_add_h) line_load_planes(L, Planes{const_cast<bf16*>(e.aux_add_h), 0, e.ld_aux}, 1, m0w, nc, n_st, 1.0f, ad);
+    else line_load_f32(L, e.aux_add + (long long)m0w * e.ld_aux + nc, e.ld_aux, n_st, ad);
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] += ad[i];
   }

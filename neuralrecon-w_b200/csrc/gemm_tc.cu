@@ -607,19 +607,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
-    static_assert(N_EPI_WARPS == 16, "prefetch_aux_tile maps 16 warps x 8 lanes onto the 128 rows of a tile");
-    if (EK != EK_GENERIC && unit < n_items && p.k_slices == 1)
-      prefetch_aux_tile<EK>(p.epi, (unit / p.n_tiles) * (2 * BM) + (int)rank * BM, (unit % p.n_tiles) * BN2, p.M, p.N, ew, lane);
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
       const int n0 = (t % p.n_tiles) * BN2;
       const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
-      if (EK != EK_GENERIC && p.k_slices == 1 && item + n_units < n_items) {   // aux streams of the NEXT tile -> L2
-        const int tn = item + n_units;
-        prefetch_aux_tile<EK>(p.epi, (tn / p.n_tiles) * (2 * BM) + (int)rank * BM, (tn % p.n_tiles) * BN2, p.M, p.N, ew, lane);
-      }
       if (use_cs && n0 != cs_n0) {
         if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
         cs_n0 = n0;
@@ -810,13 +803,14 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   L.mma_flops = L.flops * n_products(g.n_planes);
   L.M = g.M; L.N = g.N; L.K = g.K; L.P = g.n_planes; L.mn = g.mn_major; L.ks = g.k_slices;
   const Epi& e = g.epi;
-  L.epi = (e.out_pre ? 1u : 0u) | (e.out_f32 ? 2u : 0u) | (e.out2 ? 4u : 0u) | (e.n_planes ? 8u : 0u) | ((e.aux_sig || e.aux_u.p) ? 16u : 0u) |
-          ((e.aux_q && !e.aux_q_bcast) ? 32u : 0u) | (e.aux_add ? 64u : 0u) | (e.aux_relu ? 128u : 0u) | (e.atomic ? 256u : 0u) |
+  L.epi = ((e.out_pre || e.out_pre_h) ? 1u : 0u) | (e.out_f32 ? 2u : 0u) | ((e.out2 || e.out2_h) ? 4u : 0u) | (e.n_planes ? 8u : 0u) | ((e.aux_sig || e.aux_u.p) ? 16u : 0u) |
+          (((e.aux_q && !e.aux_q_bcast) || e.aux_q_h) ? 32u : 0u) | ((e.aux_add || e.aux_add_h) ? 64u : 0u) | (e.aux_relu ? 128u : 0u) | (e.atomic ? 256u : 0u) |
           (e.colsum ? 512u : 0u);
   const double mn = (double)g.M * (double)std::min(g.N, e.n_store);
-  L.bytes = 2.0 * g.n_planes * ((double)g.M * g.K + (double)g.N * g.K) + (e.out_pre ? 4.0 * g.M * g.N : 0.0) +
+  L.bytes = 2.0 * g.n_planes * ((double)g.M * g.K + (double)g.N * g.K) + (e.out_pre ? 4.0 * g.M * g.N : 0.0) + (e.out_pre_h ? 2.0 * g.M * g.N : 0.0) +
             mn * (4.0 * ((e.out_f32 ? 1 : 0) + (e.out2 ? 1 : 0) + (e.aux_sig ? 1 : 0) + ((e.aux_q && !e.aux_q_bcast) ? 1 : 0) +
-                         (e.aux_add ? 1 : 0)) + 2.0 * e.n_planes + (e.aux_relu ? 2.0 : 0.0) + (e.aux_u.p ? 2.0 * e.aux_u_planes : 0.0));
+                         (e.aux_add ? 1 : 0)) + 2.0 * e.n_planes + (e.aux_relu ? 2.0 : 0.0) + (e.aux_u.p ? 2.0 * e.aux_u_planes : 0.0) +
+                  2.0 * ((e.out2_h ? 1 : 0) + (e.aux_q_h ? 1 : 0) + (e.aux_add_h ? 1 : 0)));
   NRW_CUDA_OK(cudaEventRecord(L.e0, stream));
   const int rc = gemm_tc_impl(g, stream);
   NRW_CUDA_OK(cudaEventRecord(L.e1, stream));

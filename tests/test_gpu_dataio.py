@@ -176,9 +176,19 @@ def test_sdf_volume_matches_pointwise_queries():
     r = build_system(P, cfg, precision="bf16x3", backend=0, chunk_rows=8192)["renderer"]
     dim = 24
     vol, vol_origin, voxel = sdf_volume(r, dim, origin=(0.1, 0.0, -0.05), radius=0.9, chunk=5000)
+    # exact against pointwise queries on the kernel's own lattice (chunking invariance of the pipeline) ...
+    from nrw import _lib
+    L = _lib.lib()
+    o64 = np.array((0.1, 0.0, -0.05), dtype=np.float64)
+    lo, hi = (o64 - 0.9).astype(np.float32), (o64 + 0.9).astype(np.float32)
+    pts = torch.zeros(dim ** 3, 3, device="cuda")
+    _lib.check(L.nrw_grid_points_dense(dim, _f3(lo), _f3(hi), 0, dim ** 3, _lib.ptr(pts), _lib.stream_ptr()), "dense")
+    own = r.sdf(pts.reshape(-1, 1, 3)).reshape(-1)
+    assert vol.shape == (dim, dim, dim) and torch.equal(vol.reshape(-1), own), float((vol.reshape(-1) - own).abs().max())
+    # ... and equal to the queries on torch's CPU-built lattice up to the effect of its 1-ulp coordinate differences
+    # (see test_dense_lattice_bitexact; sin(32 x) amplifies an ulp of x by 32)
     want = r.sdf(dp.dense_lattice(dim, (0.1, 0.0, -0.05), 0.9).cuda().reshape(-1, 1, 3)).reshape(dim, dim, dim)
-    # (lattice coordinates agree with torch's CPU linspace to 1 ulp, see test_dense_lattice_bitexact)
-    assert vol.shape == (dim, dim, dim) and float((vol - want).abs().max()) < 2e-6
+    assert float((vol - want).abs().max()) < 5e-4, float((vol - want).abs().max())
     assert abs(voxel - 2 * 0.9 / (dim - 1)) < 1e-12 and np.allclose(vol_origin, np.array([0.1, 0.0, -0.05]) - 0.9)
     # sanity of the field itself: geometric-init-like sphere of radius ~0.5
     c = dim // 2
