@@ -55,7 +55,30 @@ inline int pick_epi_kind(const Epi& e) {
   return EK_GENERIC;
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Side-stream loads of the epilogue.  The four epilogue warps of a TMEM lane quarter read NEIGHBOURING 64-byte (fp32) /
+// 32-byte (bf16) pieces of the same rows, so the first of them asks L2 to fetch the whole aligned 256 bytes
+// (ld.global.nc.L2::256B): the other three find their sectors in L2 instead of queueing a second HBM round trip.
+#ifndef NRW_EPI_L2_256B
+#define NRW_EPI_L2_256B 1
+#endif
+__device__ __forceinline__ float4 ldg4(const float* p) {
+#if NRW_EPI_L2_256B
+  float4 v;
+  asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const float4*>(p));
+#endif
+}
+__device__ __forceinline__ uint2 ldg2u(const bf16* p) {
+#if NRW_EPI_L2_256B
+  uint2 v;
+  asm volatile("ld.global.nc.L2::256B.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const uint2*>(p));
+#endif
+}
 __device__ __forceinline__ void unpack_bf16x4(const uint2 t, float (&o)[4]) {
   o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xFFFF0000u);
   o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xFFFF0000u);
@@ -114,14 +137,14 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
       const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) ru0[it] = __ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld));
+      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(up + (long long)it * 8 * e.aux_u.ld);
     }
     if constexpr (EK == EK_TANGENT) {
       if (e.aux_q_h) {
         const bf16* qp = e.aux_q_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(qp + (long long)it * 8 * e.ld_aux));
+          const uint2 t = ldg2u(qp + (long long)it * 8 * e.ld_aux);
           rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
         }
       } else if (!e.aux_q_bcast) {
@@ -139,7 +162,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
         const bf16* ap = e.aux_add_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ap + (long long)it * 8 * e.ld_aux));
+          const uint2 t = ldg2u(ap + (long long)it * 8 * e.ld_aux);
           rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
         }
       } else {
@@ -151,7 +174,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     if constexpr (EK == EK_RELU_BWD) {
       const bf16* rp = e.aux_relu + row * e.ld_relu + col;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) ru0[it] = __ldg(reinterpret_cast<const uint2*>(rp + (long long)it * 8 * e.ld_relu));
+      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(rp + (long long)it * 8 * e.ld_relu);
     }
     // ---- the one transpose: row layout -> line layout (identical to epi_chunk16) ----
 #pragma unroll
@@ -222,7 +245,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float t4[4];
-          unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(up + (long long)it * 8 * e.aux_u.ld)), t4);
+          unpack_bf16x4(ldg2u(up + (long long)it * 8 * e.aux_u.ld), t4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
         }

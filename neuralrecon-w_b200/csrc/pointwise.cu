@@ -186,29 +186,27 @@ int launch_head(int nout, Planes X, int n_planes, int K, int M, const float* W, 
 //   mode 2: NeRF alpha head: dpre = g_alpha * exp(-softplus(density)*dist) * dist * sigmoid(density)
 // writes dX[m,k] = relu'(X[m,k]) * sum_c dpre[m,c] W[c,k] as planes (or, when dX.p == null, only dpre to
 // dpre_out), and accumulates dW[c,k] += sum_m dpre X, db[c] += sum_m dpre with block-level partials.
+// One block = HB_ROWS rows; thread t owns the column PAIR (2t, 2t+1) (4-byte bf16x2 accesses, K/2 threads): the per-row
+// pre-activation gradients dpre sit in shared memory, the dW partials of the block stay in registers and leave with one
+// global atomic per (column, output) - no shared-memory atomics (the first version spent 3 of them per element).
+static constexpr int HB_ROWS = 128;
 template <int NOUT>
-__global__ void __launch_bounds__(256) head_bwd_kernel(Planes X, int n_planes, int K, int M,
+__global__ void __launch_bounds__(128) head_bwd_kernel(Planes X, int n_planes, int K, int M,
                                                        const float* __restrict__ W,
                                                        const float* __restrict__ g_out,
                                                        const float* __restrict__ y_or_density,
                                                        const float* __restrict__ dists, int mode, Planes dX,
                                                        float* __restrict__ dpre_out, float* __restrict__ dW,
                                                        float* __restrict__ db) {
-  extern __shared__ float sm[];  // [NOUT*K] partial dW, [NOUT] partial db
-  float* sW = sm;
-  float* sb = sm + NOUT * K;
-  for (int i = threadIdx.x; i < NOUT * K + NOUT; i += blockDim.x) sm[i] = 0.0f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int rows_per_block = 64;
-  const int row0 = blockIdx.x * rows_per_block;
-  for (int rr = wib; rr < rows_per_block; rr += wpb) {
-    const int m = row0 + rr;
-    if (m >= M) break;
-    float dp[NOUT];
-#pragma unroll
-    for (int c = 0; c < NOUT; ++c) {
-      float g = g_out[(long long)m * NOUT + c];
+  __shared__ float sdp[HB_ROWS][NOUT];
+  const int row0 = blockIdx.x * HB_ROWS;
+  const int nrows = min(HB_ROWS, M - row0);
+  for (int i = threadIdx.x; i < HB_ROWS * NOUT; i += blockDim.x) {
+    const int r = i / NOUT, c = i % NOUT;
+    float g = 0.0f;
+    if (r < nrows) {
+      const int m = row0 + r;
+      g = g_out[(long long)m * NOUT + c];
       if (mode == 1) {
         const float y = y_or_density[(long long)m * NOUT + c];
         g = g * y * (1.0f - y);
@@ -218,37 +216,58 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(Planes X, int n_planes, i
         const float dsp = dens > 20.0f ? 1.0f : sigmoidf_(dens);
         g = g * expf(-sp * dists[m]) * dists[m] * dsp;
       }
-      dp[c] = g;
+      if (dpre_out) dpre_out[(long long)m * NOUT + c] = g;
     }
-    if (dpre_out && lane < NOUT) dpre_out[(long long)m * NOUT + lane] = dp[lane < NOUT ? lane : 0];
-    for (int j = lane; j < K; j += 32) {
-      const float x = planes_load(X, n_planes, (long long)m * X.ld + j);
-      float acc = 0.0f;
-#pragma unroll
-      for (int c = 0; c < NOUT; ++c) {
-        acc = fmaf(dp[c], W[c * K + j], acc);
-        atomicAdd(&sW[c * K + j], dp[c] * x);
-      }
-      if (dX.p) planes_store(dX, n_planes, (long long)m * dX.ld + j, x > 0.0f ? acc : 0.0f);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < NOUT; ++c) atomicAdd(&sb[c], dp[c]);
-    }
+    sdp[r][c] = g;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) atomicAdd(&dW[i], sW[i]);
-  if (threadIdx.x < NOUT) atomicAdd(&db[threadIdx.x], sb[threadIdx.x]);
+  if (threadIdx.x < NOUT) {                       // bias gradient of this block
+    float sacc = 0.0f;
+    for (int r = 0; r < nrows; ++r) sacc += sdp[r][threadIdx.x];
+    atomicAdd(&db[threadIdx.x], sacc);
+  }
+  const int j = threadIdx.x * 2;
+  if (j >= K) return;
+  float w0[NOUT], w1[NOUT], a0[NOUT], a1[NOUT];
+#pragma unroll
+  for (int c = 0; c < NOUT; ++c) { w0[c] = W[c * K + j]; w1[c] = W[c * K + j + 1]; a0[c] = a1[c] = 0.0f; }
+  for (int r = 0; r < nrows; ++r) {
+    const long long off = (long long)(row0 + r) * X.ld + j;
+    float x0 = 0.0f, x1 = 0.0f;
+    for (int pl = 0; pl < n_planes; ++pl) {
+      const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(X.plane(pl) + off));
+      x0 += __uint_as_float(t << 16);
+      x1 += __uint_as_float(t & 0xFFFF0000u);
+    }
+    float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) {
+      const float dp = sdp[r][c];
+      d0 = fmaf(dp, w0[c], d0); d1 = fmaf(dp, w1[c], d1);
+      a0[c] = fmaf(dp, x0, a0[c]); a1[c] = fmaf(dp, x1, a1[c]);
+    }
+    if (dX.p) {
+      float v[2] = {x0 > 0.0f ? d0 : 0.0f, x1 > 0.0f ? d1 : 0.0f};
+      const long long doff = (long long)(row0 + r) * dX.ld + j;
+      for (int pl = 0; pl < n_planes; ++pl) {
+        uint32_t pk[1];
+        split_plane<2>(v, pk);
+        *reinterpret_cast<uint32_t*>(dX.plane(pl) + doff) = pk[0];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NOUT; ++c) { atomicAdd(&dW[c * K + j], a0[c]); atomicAdd(&dW[c * K + j + 1], a1[c]); }
 }
 int launch_head_bwd(int nout, Planes X, int n_planes, int K, int M, const float* W, const float* g_out,
                     const float* y_or_density, const float* dists, int mode, Planes dX, float* dpre_out,
                     float* dW, float* db, cudaStream_t s) {
-  const int grid = cdiv(M, 64);
-  const size_t smem = (size_t)(nout * K + nout) * sizeof(float);
+  NRW_CHECK(K % 2 == 0 && K <= 256 && (X.ld & 1) == 0 && (dX.p == nullptr || (dX.ld & 1) == 0), NRW_ERR_ARG, "head_bwd: K=%d", K);
+  const int grid = cdiv(M, HB_ROWS);
   if (nout == 1)
-    head_bwd_kernel<1><<<grid, 256, smem, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
+    head_bwd_kernel<1><<<grid, 128, 0, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
   else
-    head_bwd_kernel<3><<<grid, 256, smem, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
+    head_bwd_kernel<3><<<grid, 128, 0, s>>>(X, n_planes, K, M, W, g_out, y_or_density, dists, mode, dX, dpre_out, dW, db);
   NRW_LAUNCH_OK();
   return NRW_OK;
 }

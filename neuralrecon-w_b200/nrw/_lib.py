@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnrw.so")
+LIB_PATH = os.environ.get("NRW_LIB_PATH") or os.path.join(_HERE, "libnrw.so")     # NRW_LIB_PATH: A/B builds (tools/)
 
 NRW_GEMM_TCGEN05 = 0
 NRW_GEMM_SIMT = 1
