@@ -114,8 +114,12 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
   }
 }
 
-// (A bulk L2 prefetch of the next tile's auxiliary streams, cp.async.bulk.prefetch.L2 issued one tile ahead, was measured
-//  SLOWER on the same box - 102.5 vs 98.0 ms of GEMM time per step - and removed.)
+// Two prefetch schemes for the side streams were built, measured on the same box and REMOVED because they were slower:
+//  * cp.async.bulk.prefetch.L2 of the next tile's streams issued one tile ahead: 102.5 vs 98.0 ms of GEMM time per step;
+//  * cp.async (LDGSTS, 8 bytes per lane) of the next chunk's streams into lane-private shared-memory slots, double
+//    buffered: reverse sweep 343 -> 490 us, tangent sweep 387 -> 518 us per launch (git history: 'Epilogue side streams
+//    prefetched one chunk ahead with cp.async').
+// What did help: ld.global.nc.L2::256B on these loads (-1.2 % step time) and hoisting them above the transpose.
 // ---- register-free prefetch of the side streams: cp.async into lane-private shared-memory slots ------------------------
 // The epilogue warps are bound by the number of side-stream bytes they keep in flight (16 warps x one 32 x 16 chunk).
 // With a 2 KB double-buffered slot per warp the loads of chunk k+1 are issued BEFORE chunk k is processed, without
