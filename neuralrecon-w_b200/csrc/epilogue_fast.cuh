@@ -120,62 +120,9 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
 //    buffered: reverse sweep 343 -> 490 us, tangent sweep 387 -> 518 us per launch (git history: 'Epilogue side streams
 //    prefetched one chunk ahead with cp.async').
 // What did help: ld.global.nc.L2::256B on these loads (-1.2 % step time) and hoisting them above the transpose.
-// ---- register-free prefetch of the side streams: cp.async into lane-private shared-memory slots ------------------------
-// The epilogue warps are bound by the number of side-stream bytes they keep in flight (16 warps x one 32 x 16 chunk).
-// With a 2 KB double-buffered slot per warp the loads of chunk k+1 are issued BEFORE chunk k is processed, without
-// spending registers: every lane copies the 4 x 8 bytes it will need itself (its 4 rows x 4 bf16 columns of stream 0 at
-// [it][lane], of stream 1 at 1024 + [it][lane]) and reads them back after cp.async.wait_group - no cross-lane traffic,
-// no bank conflicts (consecutive lanes, consecutive 8-byte slots).
-//   stream 0: first gate plane (GATE_FWD / TANGENT / REVERSE) or the ReLU plane (RELU_BWD)
-//   stream 1: second gate plane (GATE_FWD), aux_q_h (TANGENT), aux_add_h (REVERSE)
-static constexpr int AUX_SLOT_BYTES = 2048;
-__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ bool epi_fast_eligible(const Epi& e, int m0w, int nc, int M, int N) {
-  return M - m0w >= 32 && N - nc >= 16 && e.n_store - nc >= 16;
-}
-template <int EK>
-__device__ __forceinline__ void aux_issue(const Epi& e, int aux_mask, uint32_t slot, int m0w, int nc, int lane) {
-  const int sl = lane & 3, r0 = lane >> 2;
-  const int col = nc + sl * 4;
-  const long long row = (long long)m0w + r0;
-  const bf16* s0;
-  long long ld0;
-  if constexpr (EK == EK_RELU_BWD) { s0 = e.aux_relu; ld0 = e.ld_relu; }
-  else { s0 = e.aux_u.p; ld0 = e.aux_u.ld; }
-  const bf16* p0 = s0 + row * ld0 + col;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) cp_async8(slot + (it * 32 + lane) * 8, p0 + (long long)it * 8 * ld0);
-  if (aux_mask & 2) {
-    const bf16* s1;
-    long long ld1;
-    if constexpr (EK == EK_GATE_FWD) { s1 = e.aux_u.p + e.aux_u.pstride; ld1 = e.aux_u.ld; }
-    else if constexpr (EK == EK_TANGENT) { s1 = e.aux_q_h; ld1 = e.ld_aux; }
-    else { s1 = e.aux_add_h; ld1 = e.ld_aux; }
-    const bf16* p1 = s1 + row * ld1 + col;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) cp_async8(slot + 1024 + (it * 32 + lane) * 8, p1 + (long long)it * 8 * ld1);
-  }
-}
-// host: can the side streams of `e` (kind ek) be staged in 2 KB per chunk?  returns the stream mask (0 = no)
-inline int pick_aux_stage(const Epi& e, int ek) {
-  switch (ek) {
-    case EK_GATE_FWD: return e.aux_u_planes == 1 ? 1 : (e.aux_u_planes == 2 ? 3 : 0);
-    case EK_TANGENT: return (e.aux_u_planes == 1 && e.aux_q_h) ? 3 : ((e.aux_u_planes == 1 && e.aux_q_bcast) ? 1 : 0);
-    case EK_REVERSE: return (e.aux_u_planes == 1 && e.aux_add_h) ? 3 : 0;
-    case EK_RELU_BWD: return 1;
-    default: return 0;
-  }
-}
-
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
-                                           float* cs_tile, const uint8_t* sa = nullptr, int aux_mask = 0) {
+                                           float* cs_tile) {
   if constexpr (EK == EK_GENERIC) {
     epi_chunk16(e, stg, v, m0w, nc, M, N, lane, cs_tile);
     return;
@@ -191,29 +138,13 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     // ---- auxiliary streams first (raw registers): their latency overlaps the transpose below ----
     uint2 ru0[4];                     // first gate plane (further planes are loaded in place below)
     float4 rf[4];                     // fp32 side stream (aux_q / aux_add), or its bf16 twin's raw bits in .x/.y
-    const bool staged = sa != nullptr;                // side streams already in this lane's shared-memory slots (cp.async)
-    if (staged) {
-#pragma unroll
-      for (int it = 0; it < 4; ++it) ru0[it] = *reinterpret_cast<const uint2*>(sa + (it * 32 + lane) * 8);
-      if ((aux_mask & 2) && EK != EK_GATE_FWD) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const uint2 t = *reinterpret_cast<const uint2*>(sa + 1024 + (it * 32 + lane) * 8);
-          rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
-        }
-      }
-    }
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
-      if (!staged) {
-        const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
+      const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(up + (long long)it * 8 * e.aux_u.ld);
-      }
+      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(up + (long long)it * 8 * e.aux_u.ld);
     }
     if constexpr (EK == EK_TANGENT) {
-      if (staged && (aux_mask & 2)) {
-        // aux_q_h came through the staging slot
-      } else if (e.aux_q_h) {
+      if (e.aux_q_h) {
         const bf16* qp = e.aux_q_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -231,9 +162,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_REVERSE) {
-      if (staged && (aux_mask & 2)) {
-        // aux_add_h came through the staging slot
-      } else if (e.aux_add_h) {
+      if (e.aux_add_h) {
         const bf16* ap = e.aux_add_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -247,11 +176,9 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_RELU_BWD) {
-      if (!staged) {
-        const bf16* rp = e.aux_relu + row * e.ld_relu + col;
+      const bf16* rp = e.aux_relu + row * e.ld_relu + col;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(rp + (long long)it * 8 * e.ld_relu);
-      }
+      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(rp + (long long)it * 8 * e.ld_relu);
     }
     // ---- the one transpose: row layout -> line layout (identical to epi_chunk16) ----
 #pragma unroll
@@ -317,13 +244,12 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
 #pragma unroll
         for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
       }
-      for (int pl = 1; pl < e.aux_u_planes; ++pl) {         // further planes: staged (GATE_FWD, plane 1) or loaded in place
+      for (int pl = 1; pl < e.aux_u_planes; ++pl) {         // further planes: loaded in place
         const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
-        const bool from_slot = EK == EK_GATE_FWD && staged && pl == 1 && (aux_mask & 2);
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float t4[4];
-          unpack_bf16x4(from_slot ? *reinterpret_cast<const uint2*>(sa + 1024 + (it * 32 + lane) * 8) : ldg2u(up + (long long)it * 8 * e.aux_u.ld), t4);
+          unpack_bf16x4(ldg2u(up + (long long)it * 8 * e.aux_u.ld), t4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
         }
@@ -331,7 +257,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       const float kk = NRW_GATE_K * e.aux_u_scale, sc = e.scale;
       if constexpr (EK == EK_TANGENT) {
         float q[16];
-        if (e.aux_q_h) {           // (staged or loaded: raw bf16 bits in rf[it].x/.y)
+        if (e.aux_q_h) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             float t4[4];

@@ -30,7 +30,6 @@ namespace nrw {
 static constexpr int BM = 128;
 static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 static constexpr int STAGE_BUDGET = 192 * 1024;
-static constexpr int AUX_SPLIT = 128 * 1024;       // with side-stream staging: operand ring [0, 128 KB), staging slots [128 KB, 192 KB)
 static constexpr int MAX_STAGES = 8;
 static constexpr int N_EPI_WARPS = 16;          // 4 per TMEM lane quarter, 16-column chunks (epilogue_tc.cuh)
 static constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
@@ -52,7 +51,6 @@ struct TcParams {
   //  [3] epilogue warp 4: waiting for the accumulator   [4] epilogue warp 4: busy   [5] kernel cycles   [6] tiles
   unsigned long long* prof;
   int dbg;   // tuning experiments (NRW_TC_DBG): bit0 = epilogue only drains TMEM, bit1 = one MMA per k-block
-  int aux_stage;   // CTA-pair kernel: side streams of the epilogue prefetched by cp.async into shared memory (stream mask; 0 = off)
 };
 #define NRW_PROF_T0(cond) const long long _t0 = (cond) ? clock64() : 0
 #define NRW_PROF_ADD(cond, slot) \
@@ -445,8 +443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
-  const bool aux_on = EK != EK_GENERIC && p.aux_stage != 0;
-  int stages = (aux_on ? AUX_SPLIT : STAGE_BUDGET) / stage_bytes;
+  int stages = STAGE_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
@@ -610,21 +607,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
-    // side-stream staging (epilogue_fast.cuh): this warp's two 2 KB slots, chunk counter, and the very first chunk's loads
-    const uint8_t* aux_gen = smem + AUX_SPLIT + ew * (2 * AUX_SLOT_BYTES);
-    const uint32_t aux_slot = smem_u32(aux_gen);
-    int aux_k = 0, pred_m0w = 0, pred_nc = 0;
-    bool pred_ok = false, cur_staged = false;
-    if (aux_on) {
-      if (unit < n_items) {
-        const int t0 = unit / p.k_slices;
-        pred_m0w = (t0 / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
-        pred_nc = (t0 % p.n_tiles) * BN2 + chalf * 16;
-        pred_ok = pred_nc < p.N && epi_fast_eligible(p.epi, pred_m0w, pred_nc, p.M, p.N);
-        if (pred_ok) aux_issue<EK>(p.epi, p.aux_stage, aux_slot, pred_m0w, pred_nc, lane);
-      }
-      cp_async_commit();
-    }
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
@@ -648,33 +630,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
         for (int c = chalf; c < BN2 / 16; c += CH_PER) {
           const int nc = n0 + c * 16;
           if (nc >= p.N) break;
-          const int m0w = m0 + quarter * 32;
-          if (aux_on) {
-            // side streams of the NEXT chunk this warp will process (same tile, or the first one of its next tile)
-            int nm0w = m0w, nnc = nc + CH_PER * 16;
-            bool have = (c + CH_PER < BN2 / 16) && nnc < p.N;
-            if (!have && item + n_units < n_items) {
-              const int tn = (item + n_units) / p.k_slices;
-              nm0w = (tn / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
-              nnc = (tn % p.n_tiles) * BN2 + chalf * 16;
-              have = nnc < p.N;
-            }
-            const bool cur_ok = pred_ok && pred_m0w == m0w && pred_nc == nc;   // the slot really holds THIS chunk
-            pred_ok = have && epi_fast_eligible(p.epi, nm0w, nnc, p.M, p.N);
-            pred_m0w = nm0w; pred_nc = nnc;
-            if (pred_ok) aux_issue<EK>(p.epi, p.aux_stage, aux_slot + ((aux_k + 1) & 1) * AUX_SLOT_BYTES, nm0w, nnc, lane);
-            cp_async_commit();
-            cur_staged = cur_ok;
-          }
           float v[16];
           tmem_ld16(tmem_base + acc * BN2 + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
-          const uint8_t* sa = nullptr;
-          if (aux_on) {
-            cp_async_wait<1>();          // everything but the group just committed: this chunk's slot is filled
-            if (cur_staged) sa = aux_gen + (aux_k & 1) * AUX_SLOT_BYTES;
-            ++aux_k;
-          }
-          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0w, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr, sa, p.aux_stage);
+          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
         }
       }
       tc_fence_before();
@@ -901,11 +859,6 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     if (items < pairs) pairs = items;
     static const int use_fast = getenv("NRW_EPI_FAST") ? atoi(getenv("NRW_EPI_FAST")) : 1;   // 0: generic epilogue everywhere
     const int ek = (g.mn_major || !use_fast) ? EK_GENERIC : pick_epi_kind(g.epi);
-    // side-stream staging needs >= 2 operand stages in the 128 KB that remain, a non-split-K launch, and a kind-specific
-    // stream set of <= 2 KB per chunk; NRW_AUX_STAGE is a per-kind bit mask for A/B runs (default: every kind)
-    static const int aux_kinds = getenv("NRW_AUX_STAGE") ? atoi(getenv("NRW_AUX_STAGE")) : ~0;
-    const int stage_bytes = g.n_planes * (BM * BK * 2 + (BN2 / 2) * BK * 2);
-    p.aux_stage = (ek != EK_GENERIC && g.k_slices == 1 && 2 * stage_bytes <= AUX_SPLIT && ((aux_kinds >> ek) & 1)) ? pick_aux_stage(g.epi, ek) : 0;
     if (g.mn_major) { NRW_TRY((launch2<1, EK_GENERIC>(p, pairs, dev, stream))); }
     else {
       switch (ek) {
