@@ -120,9 +120,38 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
 //    buffered: reverse sweep 343 -> 490 us, tangent sweep 387 -> 518 us per launch (git history: 'Epilogue side streams
 //    prefetched one chunk ahead with cp.async').
 // What did help: ld.global.nc.L2::256B on these loads (-1.2 % step time) and hoisting them above the transpose.
+__device__ __forceinline__ bool epi_fast_eligible(const Epi& e, int m0w, int nc, int M, int N) {
+  return M - m0w >= 32 && N - nc >= 16 && e.n_store - nc >= 16;
+}
+// host: the (at most two) bf16 side streams of kind `ek` that fit the 2 KB staging slot of a chunk: pointer + leading dimension
+// of stream 0 / stream 1; returns the stream mask (0 = this launch keeps the register loads)
+inline int pick_aux_streams(const Epi& e, int ek, const bf16** p0, int* ld0, const bf16** p1, int* ld1) {
+  *p0 = *p1 = nullptr; *ld0 = *ld1 = 0;
+  switch (ek) {
+    case EK_GATE_FWD:
+      if (e.aux_u_planes < 1 || e.aux_u_planes > 2) return 0;
+      *p0 = e.aux_u.p; *ld0 = e.aux_u.ld;
+      if (e.aux_u_planes == 2) { *p1 = e.aux_u.p + e.aux_u.pstride; *ld1 = e.aux_u.ld; }
+      return e.aux_u_planes == 2 ? 3 : 1;
+    case EK_TANGENT:
+      if (e.aux_u_planes != 1 || !(e.aux_q_h || e.aux_q_bcast)) return 0;
+      *p0 = e.aux_u.p; *ld0 = e.aux_u.ld;
+      if (e.aux_q_h) { *p1 = e.aux_q_h; *ld1 = e.ld_aux; }
+      return e.aux_q_h ? 3 : 1;
+    case EK_REVERSE:
+      if (e.aux_u_planes != 1 || !e.aux_add_h) return 0;
+      *p0 = e.aux_u.p; *ld0 = e.aux_u.ld; *p1 = e.aux_add_h; *ld1 = e.ld_aux;
+      return 3;
+    case EK_RELU_BWD:
+      *p0 = e.aux_relu; *ld0 = e.ld_relu;
+      return 1;
+    default: return 0;
+  }
+}
+
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
-                                           float* cs_tile) {
+                                           float* cs_tile, const uint8_t* sa = nullptr, int aux_mask = 0) {
   if constexpr (EK == EK_GENERIC) {
     epi_chunk16(e, stg, v, m0w, nc, M, N, lane, cs_tile);
     return;
@@ -136,15 +165,46 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     const int col = nc + sl * 4;                      // this lane's 4 columns
     const long long row = (long long)m0w + r0;        // this lane's first row; rows row + 8*it
     // ---- auxiliary streams first (raw registers): their latency overlaps the transpose below ----
-    uint2 ru0[4];                     // first gate plane (further planes are loaded in place below)
-    float4 rf[4];                     // fp32 side stream (aux_q / aux_add), or its bf16 twin's raw bits in .x/.y
+    uint2 ru0[4];                     // first gate plane (further planes are loaded in place below, except GATE_FWD's second)
+    float4 rf[4];                     // fp32 side stream (aux_q / aux_add), or its bf16 twin's raw bits in .x/.y;
+                                      // GATE_FWD: raw bits of the SECOND gate plane in .x/.y (its own exposed round trip was
+                                      // 15 % of the stall samples, profiles/r2_gemm_fast_ncu.md); FWD_*: the bias in rf[0]
+    // `sa` != nullptr: the side streams of this chunk were brought into shared memory by TMA one chunk ahead (gemm_tc.cu):
+    // stream 0 at sa, stream 1 at sa + 1024, each a row-major [32 rows][16 columns] bf16 box (32 bytes per row)
+    const bool staged = sa != nullptr;
+    if (staged) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) ru0[it] = *reinterpret_cast<const uint2*>(sa + (it * 8 + r0) * 32 + sl * 8);
+      if (aux_mask & 2) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const uint2 t = *reinterpret_cast<const uint2*>(sa + 1024 + (it * 8 + r0) * 32 + sl * 8);
+          rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
+        }
+      }
+    }
     if constexpr (EK == EK_GATE_FWD || EK == EK_TANGENT || EK == EK_REVERSE) {
       const bf16* up = e.aux_u.p + row * e.aux_u.ld + col;
+      if (!staged) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(up + (long long)it * 8 * e.aux_u.ld);
+        for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(up + (long long)it * 8 * e.aux_u.ld);
+      }
+      if constexpr (EK == EK_GATE_FWD) {
+        if (e.aux_u_planes > 1 && !staged) {
+          const bf16* up1 = up + e.aux_u.pstride;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint2 t = ldg2u(up1 + (long long)it * 8 * e.aux_u.ld);
+            rf[it].x = __uint_as_float(t.x); rf[it].y = __uint_as_float(t.y);
+          }
+        }
+      }
     }
+    if constexpr (EK == EK_FWD_SOFTPLUS || EK == EK_FWD_RELU || EK == EK_FWD_NONE) rf[0] = ldg4(e.bias + col);
     if constexpr (EK == EK_TANGENT) {
-      if (e.aux_q_h) {
+      if (staged && (aux_mask & 2)) {
+        // aux_q_h arrived through the staging slot
+      } else if (e.aux_q_h) {
         const bf16* qp = e.aux_q_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -162,7 +222,9 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_REVERSE) {
-      if (e.aux_add_h) {
+      if (staged && (aux_mask & 2)) {
+        // aux_add_h arrived through the staging slot
+      } else if (e.aux_add_h) {
         const bf16* ap = e.aux_add_h + row * e.ld_aux + col;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -176,9 +238,11 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
       }
     }
     if constexpr (EK == EK_RELU_BWD) {
-      const bf16* rp = e.aux_relu + row * e.ld_relu + col;
+      if (!staged) {
+        const bf16* rp = e.aux_relu + row * e.ld_relu + col;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(rp + (long long)it * 8 * e.ld_relu);
+        for (int it = 0; it < 4; ++it) ru0[it] = ldg2u(rp + (long long)it * 8 * e.ld_relu);
+      }
     }
     // ---- the one transpose: row layout -> line layout (identical to epi_chunk16) ----
 #pragma unroll
@@ -196,8 +260,7 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
     float w[16];
 
     if constexpr (EK == EK_FWD_SOFTPLUS || EK == EK_FWD_RELU || EK == EK_FWD_NONE) {
-      const float4 b = ldg4(e.bias + col);
-      const float bb[4] = {b.x, b.y, b.z, b.w};
+      const float bb[4] = {rf[0].x, rf[0].y, rf[0].z, rf[0].w};     // loaded before the transpose
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float t = x[i] + bb[i & 3];
@@ -244,12 +307,13 @@ __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float
 #pragma unroll
         for (int k = 0; k < 4; ++k) u[4 * it + k] = t4[k];
       }
-      for (int pl = 1; pl < e.aux_u_planes; ++pl) {         // further planes: loaded in place
+      for (int pl = 1; pl < e.aux_u_planes; ++pl) {         // further planes: hoisted (GATE_FWD, plane 1) or loaded in place
         const bf16* up = e.aux_u.plane(pl) + row * e.aux_u.ld + col;
+        const bool hoisted = EK == EK_GATE_FWD && pl == 1;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float t4[4];
-          unpack_bf16x4(ldg2u(up + (long long)it * 8 * e.aux_u.ld), t4);
+          unpack_bf16x4(hoisted ? make_uint2(__float_as_uint(rf[it].x), __float_as_uint(rf[it].y)) : ldg2u(up + (long long)it * 8 * e.aux_u.ld), t4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) u[4 * it + k] += t4[k];
         }

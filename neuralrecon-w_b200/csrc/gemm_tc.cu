@@ -35,7 +35,10 @@ static constexpr int N_EPI_WARPS = 16;          // 4 per TMEM lane quarter, 16-c
 static constexpr int N_THREADS = 128 + 32 * N_EPI_WARPS;
 static constexpr int STG_BYTES = N_EPI_WARPS * 2048;   // per-warp 32x16 fp32 staging tiles (epilogue)
 static constexpr int CS_BYTES = 1024;                  // per-CTA column-sum accumulator (256 columns of one n-tile)
-static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + 256 + STG_BYTES + CS_BYTES;
+static constexpr int BAR_BYTES = 512;                  // 20 pipeline mbarriers + TMEM pointer, then 32 side-stream mbarriers (CTA-pair kernel)
+static constexpr int AUX_SPLIT = 128 * 1024;           // side-stream staging on: operand ring [0, 128 KB), 16 x 2 x 2 KB slots [128 KB, 192 KB)
+static constexpr int AUX_SLOT_BYTES = 2048;
+static constexpr int SMEM_BYTES = 1024 + STAGE_BUDGET + BAR_BYTES + STG_BYTES + CS_BYTES;
 static_assert(SMEM_BYTES <= 232448, "dynamic shared memory limit of sm_100");
 
 struct TcParams {
@@ -51,6 +54,8 @@ struct TcParams {
   //  [3] epilogue warp 4: waiting for the accumulator   [4] epilogue warp 4: busy   [5] kernel cycles   [6] tiles
   unsigned long long* prof;
   int dbg;   // tuning experiments (NRW_TC_DBG): bit0 = epilogue only drains TMEM, bit1 = one MMA per k-block
+  CUtensorMap tmX[2];   // CTA-pair kernel: bf16 side streams of the epilogue as [16 x 32] TMA boxes (no swizzle)
+  int aux_stage;        // stream mask (bit 0 / bit 1); 0 = the epilogue loads its side streams itself
 };
 #define NRW_PROF_T0(cond) const long long _t0 = (cond) ? clock64() : 0
 #define NRW_PROF_ADD(cond, slot) \
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256 + STG_BYTES);
+  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES + STG_BYTES);
   if (threadIdx.x < 256) cs_buf[threadIdx.x] = 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                // column interleave among warps of the same quarter
     constexpr int CH_PER = N_EPI_WARPS / 4;   // warps per quarter
-    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 512;
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
@@ -443,7 +448,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
-  int stages = STAGE_BUDGET / stage_bytes;
+  const bool aux_on = EK != EK_GENERIC && MN_MAJOR == 0 && p.aux_stage != 0;
+  int stages = (aux_on ? AUX_SPLIT : STAGE_BUDGET) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
@@ -458,6 +464,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
       tma_prefetch_desc(&p.tmA[i]);
       tma_prefetch_desc(&p.tmB[i]);
     }
+    if (aux_on) {
+      tma_prefetch_desc(&p.tmX[0]);
+      if (p.aux_stage & 2) tma_prefetch_desc(&p.tmX[1]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
@@ -468,6 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, 2 * N_EPI_WARPS);
     }
+    for (int i = 0; i < 2 * N_EPI_WARPS; ++i) mbar_init(smem_u32(bars + 32) + 8 * i, 1);   // side-stream slots: [warp][buffer]
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -476,7 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256 + STG_BYTES);
+  float* cs_buf = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES + STG_BYTES);
   if (threadIdx.x < 256) cs_buf[threadIdx.x] = 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -601,12 +612,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     const int quarter = warp & 3;
     const int chalf = ew >> 2;
     constexpr int CH_PER = N_EPI_WARPS / 4;
-    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + 256) + ew * 512;
+    float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
+    // ---- side-stream staging: this warp's two 2 KB slots + their mbarriers; a [32 x 16] bf16 TMA box per stream and chunk,
+    // issued one chunk ahead by one elected lane - deep asynchronous prefetch without registers (epilogue_fast.cuh) ----
+    const uint8_t* aux_gen = smem + AUX_SPLIT + ew * (2 * AUX_SLOT_BYTES);
+    const uint32_t aux_slot = smem_u32(aux_gen);
+    const uint32_t aux_bar = smem_u32(bars + 32) + 16 * ew;
+    const uint32_t aux_bytes = (p.aux_stage & 2) ? 2048u : 1024u;
+    uint32_t aux_ph = 0;
+    int aux_k = 0, pred_m0w = 0, pred_nc = 0;
+    bool pred_ok = false;
+    auto aux_issue = [&](int buf, int im0w, int inc) {
+      __syncwarp();                                   // every lane has read the slot's previous contents
+      if (elect_one()) {
+        const uint32_t bar = aux_bar + 8 * buf, dst = aux_slot + buf * AUX_SLOT_BYTES;
+        mbar_arrive_expect_tx(bar, aux_bytes);
+        tma_load_2d(dst, &p.tmX[0], bar, inc, im0w);
+        if (p.aux_stage & 2) tma_load_2d(dst + 1024, &p.tmX[1], bar, inc, im0w);
+      }
+      __syncwarp();
+    };
+    if (aux_on && unit < n_items) {
+      pred_m0w = (unit / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
+      pred_nc = (unit % p.n_tiles) * BN2 + chalf * 16;
+      pred_ok = pred_nc < p.N && epi_fast_eligible(p.epi, pred_m0w, pred_nc, p.M, p.N);
+      if (pred_ok) aux_issue(0, pred_m0w, pred_nc);
+    }
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
@@ -630,9 +666,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
         for (int c = chalf; c < BN2 / 16; c += CH_PER) {
           const int nc = n0 + c * 16;
           if (nc >= p.N) break;
+          const int m0w = m0 + quarter * 32;
+          const uint8_t* sa = nullptr;
+          if (aux_on) {
+            // (1) is the slot of THIS chunk valid?  (2) issue the TMA loads of the NEXT chunk this warp will process (same
+            // tile, or the first one of its next tile) into the other buffer; (3) wait for this chunk's bytes
+            const bool cur_issued = pred_ok;                               // a TMA load was issued into this chunk's buffer
+            const bool cur_ok = cur_issued && pred_m0w == m0w && pred_nc == nc;   // ... and it holds exactly this chunk
+            const int cur_buf = aux_k & 1;
+            int nm0w = m0w, nnc = nc + CH_PER * 16;
+            bool have = (c + CH_PER < BN2 / 16) && nnc < p.N;
+            if (!have && item + n_units < n_items) {
+              const int tn = item + n_units;                       // (k_slices == 1 when staging is on)
+              nm0w = (tn / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
+              nnc = (tn % p.n_tiles) * BN2 + chalf * 16;
+              have = nnc < p.N;
+            }
+            pred_ok = have && epi_fast_eligible(p.epi, nm0w, nnc, p.M, p.N);
+            pred_m0w = nm0w; pred_nc = nnc;
+            if (pred_ok) aux_issue(cur_buf ^ 1, nm0w, nnc);        // (the slot's previous contents were consumed one chunk ago)
+            if (cur_issued) {       // always consume the phase of an issued load, even if (never expected) it is not this chunk
+              mbar_wait(aux_bar + 8 * cur_buf, (aux_ph >> cur_buf) & 1u);
+              aux_ph ^= 1u << cur_buf;
+              if (cur_ok) sa = aux_gen + cur_buf * AUX_SLOT_BYTES;
+            }
+            ++aux_k;
+          }
           float v[16];
           tmem_ld16(tmem_base + acc * BN2 + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
-          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0 + quarter * 32, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr);
+          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0w, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr, sa, p.aux_stage);
         }
       }
       tc_fence_before();
@@ -694,8 +756,8 @@ static std::mutex g_map_mutex;
 
 // 2-D bf16 tensor map: inner (contiguous) x outer rows, row pitch ld elements, 128B swizzle.
 static int make_map(CUtensorMap* out, const bf16* ptr, long long inner, long long outer, long long ld,
-                    int box_inner, int box_outer) {
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+                    int box_inner, int box_outer, bool swizzle = true) {
+  MapKey key{ptr, inner, outer, ld, swizzle ? box_inner : -box_inner, box_outer};
   {
     std::lock_guard<std::mutex> lk(g_map_mutex);
     auto it = g_map_cache.find(key);
@@ -710,7 +772,7 @@ static int make_map(CUtensorMap* out, const bf16* ptr, long long inner, long lon
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NRW_CHECK(r == CUDA_SUCCESS, NRW_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld",
             (int)r, inner, outer, ld);
@@ -859,6 +921,20 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     if (items < pairs) pairs = items;
     static const int use_fast = getenv("NRW_EPI_FAST") ? atoi(getenv("NRW_EPI_FAST")) : 1;   // 0: generic epilogue everywhere
     const int ek = (g.mn_major || !use_fast) ? EK_GENERIC : pick_epi_kind(g.epi);
+    // side-stream staging by TMA: needs >= 2 operand stages in the remaining 128 KB, no split-K, and a stream set of the kind
+    // that fits 2 KB per chunk.  NRW_AUX_STAGE = per-kind bit mask for A/B runs (default: every kind)
+    static const int aux_kinds = getenv("NRW_AUX_STAGE") ? atoi(getenv("NRW_AUX_STAGE")) : ~0;
+    p.aux_stage = 0;
+    if (ek != EK_GENERIC && g.k_slices == 1 && 2 * g.n_planes * (BM * BK * 2 + (BN2 / 2) * BK * 2) <= AUX_SPLIT && ((aux_kinds >> ek) & 1)) {
+      const bf16 *x0, *x1;
+      int ld0, ld1;
+      const int mask = pick_aux_streams(g.epi, ek, &x0, &ld0, &x1, &ld1);
+      if (mask && (ld0 % 8) == 0 && (!(mask & 2) || (ld1 % 8) == 0)) {
+        NRW_TRY(make_map(&p.tmX[0], x0, ld0, g.M, ld0, 16, 32, false));
+        if (mask & 2) NRW_TRY(make_map(&p.tmX[1], x1, ld1, g.M, ld1, 16, 32, false));
+        p.aux_stage = mask;
+      }
+    }
     if (g.mn_major) { NRW_TRY((launch2<1, EK_GENERIC>(p, pairs, dev, stream))); }
     else {
       switch (ek) {
