@@ -437,8 +437,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
 
-template <int MN_MAJOR, int EK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+// NEW = number of epilogue warps (16, or 8 with more registers per thread and a 3-deep TMA prefetch of the side streams)
+template <int MN_MAJOR, int EK, int NEW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  static_assert(NEW == 16 || NEW == 8, "epilogue warps: 4 or 2 per TMEM lane quarter");
+  constexpr int NBUF = 32 / NEW;                   // staging buffers per epilogue warp (64 KB / NEW / 2 KB)
   constexpr int A_TILE = BM * BK * 2;              // this CTA's 128 rows of A
   constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
   constexpr int TMEM_COLS = 2 * BN2;               // two 256-column accumulators
@@ -448,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
-  const bool aux_on = EK != EK_GENERIC && MN_MAJOR == 0 && p.aux_stage != 0;
+  const bool aux_on = NEW == 8 && EK != EK_GENERIC && MN_MAJOR == 0 && p.aux_stage != 0;   // staging lives in the 8-warp instantiations only
   int stages = (aux_on ? AUX_SPLIT : STAGE_BUDGET) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
@@ -476,9 +479,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 2 * N_EPI_WARPS);
+      mbar_init(bar_tempty + 8 * i, 2 * NEW);
     }
-    for (int i = 0; i < 2 * N_EPI_WARPS; ++i) mbar_init(smem_u32(bars + 32) + 8 * i, 1);   // side-stream slots: [warp][buffer]
+    for (int i = 0; i < 32; ++i) mbar_init(smem_u32(bars + 32) + 8 * i, 1);   // side-stream slots: [warp][buffer]
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -606,42 +609,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + NEW) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int ew = warp - 4;
     const int quarter = warp & 3;
     const int chalf = ew >> 2;
-    constexpr int CH_PER = N_EPI_WARPS / 4;
+    constexpr int CH_PER = NEW / 4;
     float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
-    // ---- side-stream staging: this warp's two 2 KB slots + their mbarriers; a [32 x 16] bf16 TMA box per stream and chunk,
-    // issued one chunk ahead by one elected lane - deep asynchronous prefetch without registers (epilogue_fast.cuh) ----
-    const uint8_t* aux_gen = smem + AUX_SPLIT + ew * (2 * AUX_SLOT_BYTES);
+    // ---- side-stream staging: this warp's NBUF 2 KB slots + their mbarriers; a [32 x 16] bf16 TMA box per stream and
+    // chunk, issued NBUF-1 chunks ahead by one elected lane: deep asynchronous prefetch without registers.  The issue cursor
+    // (q_item, q_c) walks exactly the chunk sequence of the loops below. ----
+    const uint8_t* aux_gen = smem + AUX_SPLIT + ew * (NBUF * AUX_SLOT_BYTES);
     const uint32_t aux_slot = smem_u32(aux_gen);
-    const uint32_t aux_bar = smem_u32(bars + 32) + 16 * ew;
-    const uint32_t aux_bytes = (p.aux_stage & 2) ? 2048u : 1024u;
-    uint32_t aux_ph = 0;
-    int aux_k = 0, pred_m0w = 0, pred_nc = 0;
-    bool pred_ok = false;
-    auto aux_issue = [&](int buf, int im0w, int inc) {
-      __syncwarp();                                   // every lane has read the slot's previous contents
-      if (elect_one()) {
+    const uint32_t aux_bar = smem_u32(bars + 32) + 8 * NBUF * ew;
+    uint32_t aux_ph = 0, aux_issued = 0;          // per-buffer phase bits / "a load is in flight or landed" bits
+    int aux_k = 0, q_k = 0, q_item = unit, q_c = chalf;
+    auto aux_issue_next = [&]() {                 // issue the loads of the chunk under the cursor (if any), advance the cursor
+      while (q_item < n_items && (q_item % p.n_tiles) * BN2 + q_c * 16 >= p.N) { q_item += n_units; q_c = chalf; }   // tile without a chunk for this warp
+      if (q_item >= n_items) return;
+      const int im0w = (q_item / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
+      const int inc = (q_item % p.n_tiles) * BN2 + q_c * 16;
+      const int buf = q_k % NBUF;
+      const bool ok = epi_fast_eligible(p.epi, im0w, inc, p.M, p.N);
+      __syncwarp();                               // every lane has read the slot's previous contents
+      if (ok && elect_one()) {
         const uint32_t bar = aux_bar + 8 * buf, dst = aux_slot + buf * AUX_SLOT_BYTES;
-        mbar_arrive_expect_tx(bar, aux_bytes);
+        mbar_arrive_expect_tx(bar, (p.aux_stage & 2) ? 2048u : 1024u);
         tma_load_2d(dst, &p.tmX[0], bar, inc, im0w);
         if (p.aux_stage & 2) tma_load_2d(dst + 1024, &p.tmX[1], bar, inc, im0w);
       }
       __syncwarp();
+      aux_issued = ok ? (aux_issued | (1u << buf)) : (aux_issued & ~(1u << buf));
+      ++q_k;
+      q_c += CH_PER;
+      if (q_c >= BN2 / 16 || (q_item % p.n_tiles) * BN2 + q_c * 16 >= p.N) { q_item += n_units; q_c = chalf; }
     };
-    if (aux_on && unit < n_items) {
-      pred_m0w = (unit / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
-      pred_nc = (unit % p.n_tiles) * BN2 + chalf * 16;
-      pred_ok = pred_nc < p.N && epi_fast_eligible(p.epi, pred_m0w, pred_nc, p.M, p.N);
-      if (pred_ok) aux_issue(0, pred_m0w, pred_nc);
+    if (aux_on) {
+#pragma unroll 1
+      for (int i = 0; i < NBUF - 1; ++i) aux_issue_next();
     }
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
@@ -650,7 +660,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
       const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
       if (use_cs && n0 != cs_n0) {
-        if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
+        if (cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * NEW, 1);
         cs_n0 = n0;
       }
       const bool prof = p.prof != nullptr && warp == 4 && lane == 0;
@@ -669,26 +679,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
           const int m0w = m0 + quarter * 32;
           const uint8_t* sa = nullptr;
           if (aux_on) {
-            // (1) is the slot of THIS chunk valid?  (2) issue the TMA loads of the NEXT chunk this warp will process (same
-            // tile, or the first one of its next tile) into the other buffer; (3) wait for this chunk's bytes
-            const bool cur_issued = pred_ok;                               // a TMA load was issued into this chunk's buffer
-            const bool cur_ok = cur_issued && pred_m0w == m0w && pred_nc == nc;   // ... and it holds exactly this chunk
-            const int cur_buf = aux_k & 1;
-            int nm0w = m0w, nnc = nc + CH_PER * 16;
-            bool have = (c + CH_PER < BN2 / 16) && nnc < p.N;
-            if (!have && item + n_units < n_items) {
-              const int tn = item + n_units;                       // (k_slices == 1 when staging is on)
-              nm0w = (tn / p.n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32;
-              nnc = (tn % p.n_tiles) * BN2 + chalf * 16;
-              have = nnc < p.N;
-            }
-            pred_ok = have && epi_fast_eligible(p.epi, nm0w, nnc, p.M, p.N);
-            pred_m0w = nm0w; pred_nc = nnc;
-            if (pred_ok) aux_issue(cur_buf ^ 1, nm0w, nnc);        // (the slot's previous contents were consumed one chunk ago)
-            if (cur_issued) {       // always consume the phase of an issued load, even if (never expected) it is not this chunk
+            aux_issue_next();                                  // the chunk NBUF-1 ahead -> the buffer consumed last iteration
+            const int cur_buf = aux_k % NBUF;
+            if ((aux_issued >> cur_buf) & 1u) {
               mbar_wait(aux_bar + 8 * cur_buf, (aux_ph >> cur_buf) & 1u);
               aux_ph ^= 1u << cur_buf;
-              if (cur_ok) sa = aux_gen + cur_buf * AUX_SLOT_BYTES;
+              sa = aux_gen + cur_buf * AUX_SLOT_BYTES;
             }
             ++aux_k;
           }
@@ -703,7 +699,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) gemm_t
       if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
-    if (use_cs && cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * N_EPI_WARPS, 1);
+    if (use_cs && cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * NEW, 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -811,14 +807,14 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   return NRW_OK;
 }
 
-template <int MN, int EK>
+template <int MN, int EK, int NEW = N_EPI_WARPS>
 static int launch2(const TcParams& p, int pairs, int dev, cudaStream_t stream) {
   static bool attr_set[MAX_DEV] = {false};
   if (!attr_set[dev]) {
-    NRW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NRW_CUDA_OK((cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     attr_set[dev] = true;
   }
-  gemm_tc2_kernel<MN, EK><<<2 * pairs, N_THREADS, SMEM_BYTES, stream>>>(p);
+  gemm_tc2_kernel<MN, EK, NEW><<<2 * pairs, 128 + 32 * NEW, SMEM_BYTES, stream>>>(p);
   return NRW_OK;
 }
 
@@ -941,10 +937,11 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         case EK_FWD_SOFTPLUS: NRW_TRY((launch2<0, EK_FWD_SOFTPLUS>(p, pairs, dev, stream))); break;
         case EK_FWD_RELU: NRW_TRY((launch2<0, EK_FWD_RELU>(p, pairs, dev, stream))); break;
         case EK_FWD_NONE: NRW_TRY((launch2<0, EK_FWD_NONE>(p, pairs, dev, stream))); break;
-        case EK_GATE_FWD: NRW_TRY((launch2<0, EK_GATE_FWD>(p, pairs, dev, stream))); break;
-        case EK_TANGENT: NRW_TRY((launch2<0, EK_TANGENT>(p, pairs, dev, stream))); break;
-        case EK_REVERSE: NRW_TRY((launch2<0, EK_REVERSE>(p, pairs, dev, stream))); break;
-        case EK_RELU_BWD: NRW_TRY((launch2<0, EK_RELU_BWD>(p, pairs, dev, stream))); break;
+        // staged side streams: 8 epilogue warps (168 registers, 3-deep TMA prefetch); otherwise 16 warps with register loads
+        case EK_GATE_FWD: if (p.aux_stage) { NRW_TRY((launch2<0, EK_GATE_FWD, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_GATE_FWD>(p, pairs, dev, stream))); } break;
+        case EK_TANGENT: if (p.aux_stage) { NRW_TRY((launch2<0, EK_TANGENT, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_TANGENT>(p, pairs, dev, stream))); } break;
+        case EK_REVERSE: if (p.aux_stage) { NRW_TRY((launch2<0, EK_REVERSE, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_REVERSE>(p, pairs, dev, stream))); } break;
+        case EK_RELU_BWD: if (p.aux_stage) { NRW_TRY((launch2<0, EK_RELU_BWD, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_RELU_BWD>(p, pairs, dev, stream))); } break;
         default: NRW_TRY((launch2<0, EK_GENERIC>(p, pairs, dev, stream)));
       }
     }
