@@ -114,11 +114,14 @@ __device__ __forceinline__ void line_colsum_add(const float (&w)[16], int lane, 
   }
 }
 
-// Two prefetch schemes for the side streams were built, measured on the same box and REMOVED because they were slower:
-//  * cp.async.bulk.prefetch.L2 of the next tile's streams issued one tile ahead: 102.5 vs 98.0 ms of GEMM time per step;
-//  * cp.async (LDGSTS, 8 bytes per lane) of the next chunk's streams into lane-private shared-memory slots, double
-//    buffered: reverse sweep 343 -> 490 us, tangent sweep 387 -> 518 us per launch (git history: 'Epilogue side streams
-//    prefetched one chunk ahead with cp.async').
+// Prefetch schemes for the side streams, all measured by same-box A/B (profiles/r2e_epilogue_staging_ab.txt):
+//  * cp.async.bulk.prefetch.L2 of the next tile's streams one tile ahead: slower (102.5 vs 98.0 ms GEMM time per step), removed;
+//  * cp.async (LDGSTS, 8 bytes per lane) into lane-private shared-memory slots, double buffered: slower (reverse sweep
+//    343 -> 490 us), removed;
+//  * TMA boxes ([32 rows x 16 columns] bf16 per stream and chunk) into per-warp slots with per-warp mbarriers, issued by an
+//    elected lane (gemm_tc.cu): with 16 warps x 96 registers the extra state spills and it is slower; with 8 epilogue warps
+//    x 168 registers and a 3-deep queue it wins for GATE_FWD (480 -> 434 us) and loses for the one-product backward kinds
+//    (two warps per scheduler no longer hide the ALU chains) - kept, enabled for GATE_FWD only.
 // What did help: ld.global.nc.L2::256B on these loads (-1.2 % step time) and hoisting them above the transpose.
 __device__ __forceinline__ bool epi_fast_eligible(const Epi& e, int m0w, int nc, int M, int N) {
   return M - m0w >= 32 && N - nc >= 16 && e.n_store - nc >= 16;

@@ -918,8 +918,11 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     static const int use_fast = getenv("NRW_EPI_FAST") ? atoi(getenv("NRW_EPI_FAST")) : 1;   // 0: generic epilogue everywhere
     const int ek = (g.mn_major || !use_fast) ? EK_GENERIC : pick_epi_kind(g.epi);
     // side-stream staging by TMA: needs >= 2 operand stages in the remaining 128 KB, no split-K, and a stream set of the kind
-    // that fits 2 KB per chunk.  NRW_AUX_STAGE = per-kind bit mask for A/B runs (default: every kind)
-    static const int aux_kinds = getenv("NRW_AUX_STAGE") ? atoi(getenv("NRW_AUX_STAGE")) : ~0;
+    // that fits 2 KB per chunk.  NRW_AUX_STAGE = per-kind bit mask (bit EK_*) for A/B runs.
+    // Measured per kind on one box (profiles/r2e_epilogue_staging_ab.txt): staging + 8 warps wins for the gradient-chain
+    // forward (3 MMA products, two gate planes: 480 -> 434 us per launch) and loses for the one-product backward kinds
+    // (reverse 343 -> 368 us, ReLU backward 140 -> 173 us), so the default stages GATE_FWD only.
+    static const int aux_kinds = getenv("NRW_AUX_STAGE") ? atoi(getenv("NRW_AUX_STAGE")) : (1 << EK_GATE_FWD);
     p.aux_stage = 0;
     if (ek != EK_GENERIC && g.k_slices == 1 && 2 * g.n_planes * (BM * BK * 2 + (BN2 / 2) * BK * 2) <= AUX_SPLIT && ((aux_kinds >> ek) & 1)) {
       const bf16 *x0, *x1;
