@@ -3,6 +3,8 @@
 // Every dense layer is one tcgen05 GEMM launch with a fused epilogue; chunks of `Mc` samples keep the
 // inter-layer activations L2-resident.  Backward recomputes the forward of a chunk into the workspace
 // and immediately consumes it, so memory is O(chunk) instead of O(batch).
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace nrw {
@@ -51,6 +53,7 @@ static void carve(nrw_ctx& c, Carver& cv, int Mc, int with_bwd, int max_rays, in
     s.Qh[0] = nullptr;
     s.FEAT = cv.planes(M, 512, P);
     s.c_sdf = cv.f32(M);
+    s.HP = cv.f32(M * 8);
     s.c_nrm = cv.f32(M * 3);
     s.IN1 = cv.planes(M, 640, P);
     s.H1 = cv.planes(M, 128, P);
@@ -199,19 +202,25 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
   c.cur_planes = c.n_planes;
   const int P = c.n_planes;
   NRW_TRY(launch_sdf_embed(pts, M, P, c.U0, c.U[4], s));
+  const float* w0 = c.f_area + c.pm.heads.sdf_w0;
+  const float* b0 = c.f_area + c.pm.heads.sdf_b0;
+  // forward-only query (sampler, NeuconWRenderer.sdf, mesh / refresh pipelines): the SDF head is fused into the epilogue of
+  // the last layer - u_8 is never written, the head kernel never reads it (CTA-pair tcgen05 kernel only: M >= 256)
+  static const int no_fused_head = getenv("NRW_FUSED_HEAD") ? !atoi(getenv("NRW_FUSED_HEAD")) : 0;
+  const bool fused_head = !need_normal && !need_feat && M >= 256 && c.backend == NRW_GEMM_TCGEN05 && !no_fused_head;
   for (int l = 0; l < 8; ++l) {
     Epi e;
     e.bias = c.bias(L_SDF0 + l);
     e.act = ACT_SOFTPLUS100;
     // (no fp32 pre-activation store: every later gate softplus'(a_l), softplus''(a_l) is recomputed from the planes of
     //  u_{l+1} = softplus(a_l) that the next layer needs anyway - common.cuh softplus100_d12_from_u)
-    e.out_pl = c.U[l + 1];
+    if (l == 7 && fused_head) { e.head_w = w0; e.head_partial = c.HP; }
+    else e.out_pl = c.U[l + 1];
     if (l == 3) { e.scale = INV_SQRT2; e.n_store = 473; }
     NRW_TRY(mm(c, l == 0 ? c.U0 : c.U[l], c.W(L_SDF0 + l), M, 512, l == 0 ? 64 : 512, e, s));
   }
-  const float* w0 = c.f_area + c.pm.heads.sdf_w0;
-  const float* b0 = c.f_area + c.pm.heads.sdf_b0;
-  NRW_TRY(launch_sdf_head(c.U[8], M, w0, b0, c.c_sdf, P, need_normal ? c.G[7] : Planes{nullptr, 0, 0}, s));
+  if (fused_head) NRW_TRY(launch_sdf_head_sum(c.HP, M, b0, c.c_sdf, s));
+  else NRW_TRY(launch_sdf_head(c.U[8], M, w0, b0, c.c_sdf, P, need_normal ? c.G[7] : Planes{nullptr, 0, 0}, s));
   if (need_feat) {
     Epi e;
     e.bias = c.bias(L_SDF8F);

@@ -14,6 +14,7 @@ struct FwdSdfSlot {
   float* Q[8];
   nrw::bf16* Qh[8];     // bf16 twin of Q[l] (l != 0, 4) when the context keeps backward-only side streams in bf16
   float *c_sdf, *c_nrm;
+  float* HP;            // [Mc, 8] row partials of the fused SDF head (forward-only queries)
   nrw::Planes IN1, H1, IN2, X[5];
   float* c_rgb;
 };
@@ -35,7 +36,7 @@ struct nrw_ctx {
   int cached_R = 0, cached_S = 0, cached_T = 0, cached_gen = 0;   // gen: nrw_render_cfg::reserved0 of that call
   void use_sdf_slot(int i) {
     const FwdSdfSlot& s = sdf_slots[i];
-    PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm;
+    PTS = s.PTS; U0 = s.U0; FEAT = s.FEAT; c_sdf = s.c_sdf; c_nrm = s.c_nrm; HP = s.HP;
     for (int l = 0; l < 9; ++l) U[l] = s.U[l];
     for (int l = 0; l < 8; ++l) { G[l] = s.G[l]; Q[l] = s.Q[l]; Qh[l] = s.Qh[l]; }
     IN1 = s.IN1; H1 = s.H1; IN2 = s.IN2; c_rgb = s.c_rgb;
@@ -65,6 +66,7 @@ struct nrw_ctx {
   nrw::bf16* DA2h[8] = {nullptr};
   bool aux_bf16 = false;     // 'mixed': Q_l (l != 0, 4) and the second-order terms DA2_l are stored as one bf16 plane
   float* c_sdf = nullptr;
+  float* HP = nullptr;
   float* c_nrm = nullptr;
   nrw::Planes IN1, H1, IN2, X[5];
   float* c_rgb = nullptr;

@@ -52,6 +52,10 @@ struct Epi {
   int n_planes = 0;
   int n_store = 1 << 30;  // column bound for out_f32 / out_pl / out2
   float* colsum = nullptr;  // += sum over rows of the main output w (bias gradient of the producing layer)
+  // fused SDF head of a forward-only query (CTA-pair kernel, kind FWD_HEAD): row partials of softplus(x + bias) . head_w over
+  // each (256-column tile, column-interleave class) -> head_partial[m*8 + slot]; nothing else is stored
+  const float* head_w = nullptr;
+  float* head_partial = nullptr;
 };
 
 // ---- vector helpers: NC consecutive floats / bf16 of one row -------------------------------------

@@ -21,6 +21,7 @@ enum EpiKind {
   EK_TANGENT,        // w = x * s1 * scale ; out2 = scale * x * q * s2 ; w -> planes | out_f32     (tangent sweep)
   EK_REVERSE,        // [x += rv * cv] ; w = x * s1 * scale + aux_add -> planes (+ column sums)    (reverse sweep)
   EK_RELU_BWD,       // [x += rv * cv] ; w = relu'(fwd) ? x * scale : 0 -> planes (+ column sums)  (ReLU nets, backward)
+  EK_FWD_HEAD,       // softplus(x + bias) . head_w row partials, NO activation store               (last SDF layer of a forward-only query)
   EK_COUNT
 };
 
@@ -28,6 +29,10 @@ enum EpiKind {
 // fast paths are verified here once per launch instead of once per chunk)
 inline int pick_epi_kind(const Epi& e) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (e.head_w || e.head_partial)
+    return (e.head_w && e.head_partial && e.bias && al16(e.bias) && al16(e.head_w) && e.act == ACT_SOFTPLUS100 && e.scale == 1.0f && e.n_planes == 0 &&
+            !e.atomic && !e.aux_sig && !e.aux_u.p && !e.rowvec && !e.aux_relu && !e.out_pre && !e.out_pre_h && !e.out2 && !e.out2_h && !e.out_f32 &&
+            !e.colsum && !e.aux_add && !e.aux_add_h && e.n_store >= (1 << 29)) ? EK_FWD_HEAD : -1;      // -1: unsupported combination
   if (e.atomic || e.aux_sig || e.n_planes > 3) return EK_GENERIC;
   if (e.n_planes > 0 && (!al16(e.out_pl.p) || (e.out_pl.ld & 3) || (e.out_pl.pstride & 7))) return EK_GENERIC;
   if (e.aux_u.p && (!al16(e.aux_u.p) || (e.aux_u.ld & 3) || (e.aux_u.pstride & 7))) return EK_GENERIC;
@@ -154,9 +159,35 @@ inline int pick_aux_streams(const Epi& e, int ek, const bf16** p0, int* ld0, con
 
 template <int EK>
 __device__ __forceinline__ void epi_fast16(const Epi& e, float* stg, const float (&v)[16], int m0w, int nc, int M, int N, int lane,
-                                           float* cs_tile, const uint8_t* sa = nullptr, int aux_mask = 0) {
+                                           float* cs_tile, const uint8_t* sa = nullptr, int aux_mask = 0, float* hacc = nullptr) {
   if constexpr (EK == EK_GENERIC) {
     epi_chunk16(e, stg, v, m0w, nc, M, N, lane, cs_tile);
+    return;
+  } else if constexpr (EK == EK_FWD_HEAD) {
+    // every row of the 32-row group is processed (rows beyond M hold zero-filled operands and are never written); only
+    // column-indexed vectors are read, so there is no ragged fallback.  hacc[it] accumulates this lane's rows over the
+    // warp's chunks of the tile in a FIXED order (deterministic SDF values).
+    const int sl = lane & 3;
+    const int col = nc + sl * 4;
+    const float4 b = ldg4(e.bias + col), hw = ldg4(e.head_w + col);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      *reinterpret_cast<float4*>(stg + lane * 16 + ((s ^ ((lane >> 1) & 3)) << 2)) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+    __syncwarp();
+    const int r0 = lane >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + r0;
+      const float4 t = *reinterpret_cast<const float4*>(stg + rr * 16 + ((sl ^ ((rr >> 1) & 3)) << 2));
+      float p = softplus100(t.x + b.x) * hw.x;
+      p = fmaf(softplus100(t.y + b.y), hw.y, p);
+      p = fmaf(softplus100(t.z + b.z), hw.z, p);
+      p = fmaf(softplus100(t.w + b.w), hw.w, p);
+      p += __shfl_xor_sync(0xFFFFFFFFu, p, 1);
+      p += __shfl_xor_sync(0xFFFFFFFFu, p, 2);
+      hacc[it] += p;
+    }
+    __syncwarp();
     return;
   } else {
     // ragged edge tile / column boundary of the stored range: the generic path handles every case

@@ -672,6 +672,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
       tc_fence_after();
       NRW_PROF_T0(prof);
       if (prof) atomicAdd(&p.prof[blockIdx.x * 16 + 6], 1ull);
+      float hacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // FWD_HEAD: this lane's rows of the fused SDF-head dot product
       if (kb1 > kb0) {
         for (int c = chalf; c < BN2 / 16; c += CH_PER) {
           const int nc = n0 + c * 16;
@@ -690,7 +691,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
           }
           float v[16];
           tmem_ld16(tmem_base + acc * BN2 + c * 16 + ((uint32_t)(quarter * 32) << 16), v);
-          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0w, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr, sa, p.aux_stage);
+          if (!(p.dbg & 1)) epi_fast16<EK>(p.epi, stg, v, m0w, nc, p.M, p.N, lane, use_cs ? cs_buf + c * 16 : nullptr, sa, p.aux_stage, hacc);
+        }
+        if (EK == EK_FWD_HEAD && (lane & 3) == 0) {   // partial[row][slot], slot = n-tile * CH_PER + column class: plain stores
+          const int slot = (n0 / BN2) * CH_PER + chalf;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = m0 + quarter * 32 + it * 8 + (lane >> 2);
+            if (row < p.M) p.epi.head_partial[(long long)row * 8 + slot] = hacc[it];
+          }
         }
       }
       tc_fence_before();
@@ -916,7 +925,9 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     int pairs = n_sm / 2;
     if (items < pairs) pairs = items;
     static const int use_fast = getenv("NRW_EPI_FAST") ? atoi(getenv("NRW_EPI_FAST")) : 1;   // 0: generic epilogue everywhere
-    const int ek = (g.mn_major || !use_fast) ? EK_GENERIC : pick_epi_kind(g.epi);
+    const int ek = (g.mn_major || (!use_fast && !g.epi.head_w)) ? EK_GENERIC : pick_epi_kind(g.epi);
+    NRW_CHECK(ek >= 0 && (ek != EK_FWD_HEAD || (g.N == 2 * BN2 && N_EPI_WARPS == 16)), NRW_ERR_ARG,
+              "gemm_tc: the fused SDF-head epilogue needs N = 512, bias + softplus and no other output");
     // side-stream staging by TMA: needs >= 2 operand stages in the remaining 128 KB, no split-K, and a stream set of the kind
     // that fits 2 KB per chunk.  NRW_AUX_STAGE = per-kind bit mask (bit EK_*) for A/B runs.
     // Measured per kind on one box (profiles/r2e_epilogue_staging_ab.txt): staging + 8 warps wins for the gradient-chain
@@ -940,6 +951,7 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         case EK_FWD_SOFTPLUS: NRW_TRY((launch2<0, EK_FWD_SOFTPLUS>(p, pairs, dev, stream))); break;
         case EK_FWD_RELU: NRW_TRY((launch2<0, EK_FWD_RELU>(p, pairs, dev, stream))); break;
         case EK_FWD_NONE: NRW_TRY((launch2<0, EK_FWD_NONE>(p, pairs, dev, stream))); break;
+        case EK_FWD_HEAD: NRW_TRY((launch2<0, EK_FWD_HEAD>(p, pairs, dev, stream))); break;
         // staged side streams: 8 epilogue warps (168 registers, 3-deep TMA prefetch); otherwise 16 warps with register loads
         case EK_GATE_FWD: if (p.aux_stage) { NRW_TRY((launch2<0, EK_GATE_FWD, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_GATE_FWD>(p, pairs, dev, stream))); } break;
         case EK_TANGENT: if (p.aux_stage) { NRW_TRY((launch2<0, EK_TANGENT, 8>(p, pairs, dev, stream))); } else { NRW_TRY((launch2<0, EK_TANGENT>(p, pairs, dev, stream))); } break;
@@ -952,6 +964,7 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     ++g_tc_launches;
     return NRW_OK;
   }
+  NRW_CHECK(!g.epi.head_w && !g.epi.head_partial, NRW_ERR_ARG, "gemm_tc: the fused SDF-head epilogue exists in the CTA-pair kernel only (M >= 256, N = 512)");
   for (int pl = 0; pl < g.n_planes; ++pl) {
     if (!g.mn_major) {
       NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);

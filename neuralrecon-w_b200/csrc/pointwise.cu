@@ -79,6 +79,19 @@ int launch_sdf_head(Planes U8, int M, const float* w0, const float* b0, float* s
   return NRW_OK;
 }
 
+// sdf = b0 + the 8 row partials the fused-head epilogue left (fixed summation order: deterministic)
+__global__ void sdf_head_sum_kernel(const float* __restrict__ hp, int M, const float* __restrict__ b0, float* __restrict__ sdf) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(hp + (long long)m * 8)), b = __ldg(reinterpret_cast<const float4*>(hp + (long long)m * 8 + 4));
+  sdf[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) + b0[0];
+}
+int launch_sdf_head_sum(const float* hp, int M, const float* b0, float* sdf, cudaStream_t s) {
+  sdf_head_sum_kernel<<<cdiv(M, 256), 256, 0, s>>>(hp, M, b0, sdf);
+  NRW_LAUNCH_OK();
+  return NRW_OK;
+}
+
 // ---- normal = J_PE(x)^T (q0[:39] + q4[473:512] / sqrt2)   -----------------------------
 __global__ void sdf_normal_kernel(const float* __restrict__ pts, const float* __restrict__ Q0,
                                   const float* __restrict__ Q4, int M, float* __restrict__ nrm) {

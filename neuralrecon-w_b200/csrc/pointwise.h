@@ -9,6 +9,7 @@ int launch_points(const float* o, const float* d, const float* z, const float* s
 int launch_sdf_embed(const float* pts, int M, int n_planes, Planes U0, Planes U4, cudaStream_t s);
 int launch_sdf_head(Planes U8, int M, const float* w0, const float* b0, float* sdf, int n_planes, Planes G7,
                     cudaStream_t s);
+int launch_sdf_head_sum(const float* head_partial, int M, const float* b0, float* sdf, cudaStream_t s);
 int launch_sdf_normal(const float* pts, const float* Q0, const float* Q4, int M, float* nrm, cudaStream_t s);
 int launch_sdf_normal_bwd(const float* pts, const float* dn, int M, int n_planes, Planes DQ0, Planes DQ4,
                           cudaStream_t s);
