@@ -1,4 +1,4 @@
-// Compile-time specialised epilogues of the CTA-pair tcgen05 GEMM for the seven layer kinds that make up > 95 % of a
+// Compile-time specialised epilogues of the CTA-pair tcgen05 GEMM for the eight layer kinds that make up > 95 % of a
 // training step.  Same arithmetic, in the same order, as the runtime-parameterised epi_chunk16 (epilogue_tc.cuh) - the
 // difference is what is NOT executed: ncu's source view of the generic epilogue showed ISETP + BRA + LOP3 + IMAD + LDC
 // (flag tests, alignment checks, 64-bit address arithmetic, ReLU bit masks) at > 50 % of all issued instructions and
