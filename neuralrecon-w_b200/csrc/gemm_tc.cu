@@ -440,7 +440,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 // NEW = number of epilogue warps (16, or 8 with more registers per thread and a 3-deep TMA prefetch of the side streams)
 template <int MN_MAJOR, int EK, int NEW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
-  static_assert(NEW == 16 || NEW == 12 || NEW == 8, "epilogue warps: 4, 3 or 2 per TMEM lane quarter");
+  static_assert(NEW == 16 || NEW == 8, "epilogue warps: 4 or 2 per TMEM lane quarter");
   constexpr int NBUF = NEW == 8 ? 4 : 2;           // 2 KB staging buffers per epilogue warp (<= 64 KB in total, 32 mbarriers)
   constexpr int A_TILE = BM * BK * 2;              // this CTA's 128 rows of A
   constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
@@ -451,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int P = p.n_planes;
   const int stage_bytes = P * (A_TILE + B_TILE);
-  const bool aux_on = NEW != 16 && EK != EK_GENERIC && MN_MAJOR == 0 && p.aux_stage != 0;   // staging lives in the 8- / 12-warp instantiations only
+  const bool aux_on = NEW != 16 && EK != EK_GENERIC && MN_MAJOR == 0 && p.aux_stage != 0;   // staging lives in the 8-warp instantiations only
   int stages = (aux_on ? AUX_SPLIT : STAGE_BUDGET) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGE_BUDGET);
@@ -934,7 +934,6 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
     // forward (3 MMA products, two gate planes: 480 -> 434 us per launch) and loses for the one-product backward kinds
     // (reverse 343 -> 368 us, ReLU backward 140 -> 173 us), so the default stages GATE_FWD only.
     static const int aux_kinds = getenv("NRW_AUX_STAGE") ? atoi(getenv("NRW_AUX_STAGE")) : (1 << EK_GATE_FWD);
-    static const int aux_warps = getenv("NRW_AUX_WARPS") ? atoi(getenv("NRW_AUX_WARPS")) : 8;
     p.aux_stage = 0;
     if (ek != EK_GENERIC && g.k_slices == 1 && 2 * g.n_planes * (BM * BK * 2 + (BN2 / 2) * BK * 2) <= AUX_SPLIT && ((aux_kinds >> ek) & 1)) {
       const bf16 *x0, *x1;
@@ -953,13 +952,12 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         case EK_FWD_RELU: NRW_TRY((launch2<0, EK_FWD_RELU>(p, pairs, dev, stream))); break;
         case EK_FWD_NONE: NRW_TRY((launch2<0, EK_FWD_NONE>(p, pairs, dev, stream))); break;
         case EK_FWD_HEAD: NRW_TRY((launch2<0, EK_FWD_HEAD>(p, pairs, dev, stream))); break;
-        // staged side streams: 8 epilogue warps (168 registers, 3-deep TMA prefetch) or 12 (128 registers, 1-deep;
-        // NRW_AUX_WARPS=12); otherwise 16 warps with register loads
-#define NRW_STAGED_CASE(KIND)                                                                        \
-  case KIND:                                                                                         \
-    if (p.aux_stage && aux_warps == 12) { NRW_TRY((launch2<0, KIND, 12>(p, pairs, dev, stream))); }  \
-    else if (p.aux_stage) { NRW_TRY((launch2<0, KIND, 8>(p, pairs, dev, stream))); }                 \
-    else { NRW_TRY((launch2<0, KIND>(p, pairs, dev, stream))); }                                     \
+        // staged side streams: 8 epilogue warps (168 registers, 3-deep TMA prefetch); otherwise 16 warps with register loads.
+        // (A 12-warp / 128-register / 1-deep variant was measured as well: no different, profiles/r2e_epilogue_staging_ab.txt.)
+#define NRW_STAGED_CASE(KIND)                                                            \
+  case KIND:                                                                             \
+    if (p.aux_stage) { NRW_TRY((launch2<0, KIND, 8>(p, pairs, dev, stream))); }          \
+    else { NRW_TRY((launch2<0, KIND>(p, pairs, dev, stream))); }                         \
     break;
         NRW_STAGED_CASE(EK_GATE_FWD)
         NRW_STAGED_CASE(EK_TANGENT)
