@@ -161,7 +161,9 @@ def sparse_sdf_volume(renderer, grid, chunk=1 << 20, sdf_fn=None):
     sdf_dense[ind[:, 0], ind[:, 1], ind[:, 2]] = res["sdf"]
     m = torch.zeros(dim, dim, dim, dtype=torch.bool, device=dev)
     m[ind[:, 0], ind[:, 1], ind[:, 2]] = True
-    r = torch.roll
-    m = (m & r(m, 1, 0) & r(m, 1, 1) & r(m, 1, 2) & r(m, (1, 1), (0, 1)) & r(m, (1, 1), (0, 2)) & r(m, (1, 1), (1, 2))
-         & r(m, (1, 1, 1), (0, 1, 2)))
+    # a marching-cubes cell (i, j, k) uses the corners (i - a, j - b, k - c), a, b, c in {0, 1} (wrap-around as torch.roll)
+    valid = m.clone()
+    for shift in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)):
+        valid &= torch.roll(m, shifts=shift, dims=(0, 1, 2))
+    m = valid
     return sdf_dense, m

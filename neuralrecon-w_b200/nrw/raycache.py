@@ -22,16 +22,15 @@ RAY_MASK_LIST = ("person", "car", "bicycle", "minibike")      # config/train_bra
 
 
 def local_split(items, world_size, rank, seed=6):
-    """DataModule._get_local_split (datasets/data.py:83-100): permute with RandomState(seed), pad by sampling with
-    replacement, contiguous slice per rank."""
-    items = list(items)
-    n = len(items)
-    perm = np.random.RandomState(seed).permutation(items)
-    if n % world_size != 0:
-        pad = np.random.RandomState(seed).choice(items, world_size - (n % world_size), replace=True)
-        perm = np.concatenate([perm, pad])
-    per = len(perm) // world_size
-    return list(perm[per * rank: per * (rank + 1)])
+    """Split names this rank loads (DataModule._get_local_split, datasets/data.py:83-100): seeded permutation, topped up to a
+    multiple of the world size by a seeded draw with replacement, equal contiguous runs per rank."""
+    names = list(items)
+    order = np.random.RandomState(seed).permutation(names)
+    shortfall = (-len(names)) % world_size
+    if shortfall:
+        order = np.concatenate([order, np.random.RandomState(seed).choice(names, shortfall, replace=True)])
+    run = len(order) // world_size
+    return list(order[run * rank: run * (rank + 1)])
 
 
 def load_split_arrays(root_dir, split_path, split_names, img_downscale=1):

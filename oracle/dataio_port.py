@@ -17,51 +17,53 @@ LABEL_IDS = {"sky": 2, "road": 6, "person": 12, "car": 20, "minibike": 116, "bic
 
 
 def local_split(items, world_size, rank, seed=6):
-    n_items = len(items)
-    items_permute = np.random.RandomState(seed).permutation(items)
-    if n_items % world_size == 0:
-        padded = items_permute
-    else:
-        padding = np.random.RandomState(seed).choice(items, world_size - (n_items % world_size), replace=True)
-        padded = np.concatenate([items_permute, padding])
-    per = len(padded) // world_size
-    return padded[per * rank: per * (rank + 1)]
+    """Which cache splits a rank loads: a seeded permutation of the split names, topped up to a multiple of the world size
+    by a seeded draw WITH replacement from the original list, then cut into equal contiguous runs."""
+    order = np.random.RandomState(seed).permutation(items)
+    shortfall = (-len(items)) % world_size
+    if shortfall:
+        order = np.concatenate([order, np.random.RandomState(seed).choice(items, shortfall, replace=True)])
+    run = len(order) // world_size
+    return order[rank * run:(rank + 1) * run]
 
 
 def getitem_batch(all_rays, all_rgbs, index):
-    """all_rays [n,12], all_rgbs [n,3] torch CPU; index int64 [B] -> dict like the collated DataLoader batch."""
-    rows = all_rays[index]
-    return {"rays": torch.cat((rows[:, :8], rows[:, 10:13]), dim=-1), "ts": rows[:, 8].long(), "rgbs": all_rgbs[index],
-            "semantics": rows[:, 9]}
+    """Cache rows -> collated training batch.  all_rays [n,12] = o3, d3, near, far, ts, label, depth, weight."""
+    picked = all_rays[index]
+    geometry, extras = picked[:, 0:8], picked[:, 10:13]          # the reference slices 10:13 of a 12-wide row -> 2 columns
+    return {"rays": torch.cat((geometry, extras), dim=-1), "ts": picked[:, 8].long(), "rgbs": all_rgbs[index],
+            "semantics": picked[:, 9]}
 
 
 def filter_batch(batch, ray_mask_list=("person", "car", "bicycle", "minibike")):
-    ts, label = batch["ts"], batch["semantics"]
-    ray_mask = torch.ones_like(ts, dtype=torch.bool)
+    """Drop the rays whose semantic label is on the black list; order of the survivors is kept."""
+    label = batch["semantics"]
+    keep = torch.ones(label.shape[0], dtype=torch.bool)
     for name in ray_mask_list or ():
-        ray_mask[LABEL_IDS[name] == label] = False
-    return {"rays": batch["rays"][ray_mask, :], "ts": ts[ray_mask], "rgbs": batch["rgbs"][ray_mask], "label": label[ray_mask]}
+        keep &= ~(label == LABEL_IDS[name])
+    return {"rays": batch["rays"][keep], "ts": batch["ts"][keep], "rgbs": batch["rgbs"][keep], "label": label[keep]}
 
 
 def dense_lattice(dim, origin=(0.0, 0.0, 0.0), radius=1.0):
-    so = np.array(origin)
-    x = torch.linspace(so[0] - radius, so[0] + radius, dim)
-    y = torch.linspace(so[1] - radius, so[1] + radius, dim)
-    z = torch.linspace(so[2] - radius, so[2] + radius, dim)
-    return torch.stack(torch.meshgrid(x, y, z, indexing="ij"), dim=-1).reshape(-1, 3)
+    """dim^3 query lattice, x slowest / z fastest, each axis a float32 torch.linspace over [c - radius, c + radius]."""
+    centre = np.array(origin)
+    axes = [torch.linspace(centre[a] - radius, centre[a] + radius, dim) for a in range(3)]
+    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, 3)
 
 
 def sparse_lattice(sparse_ind, up_times, voxel_size, vol_origin, scene_origin, scene_radius):
-    """sparse_ind int64 [m,3] (torch.nonzero order); returns (xyz_sfm, xyz_training) float32 as the reference computes them."""
-    sparse_num = sparse_ind.shape[0]
-    up = sparse_ind.repeat_interleave(up_times ** 3, dim=0) * up_times
-    k = torch.arange(0, up_times, 1)
-    up_kernal = torch.stack(torch.meshgrid(k, k, k, indexing="ij"), dim=-1).reshape(-1, 3)
-    up = up + up_kernal.repeat([sparse_num, 1])
-    xyz_sfm = up * voxel_size + vol_origin
+    """Occupied coarse cells (int64 [m,3], torch.nonzero order), each refined into up_times^3 fine cells (cell-major, then
+    the refinement offsets in ij-meshgrid order).  Returns (xyz_sfm, xyz_training) with the reference's dtype path:
+    int64 index * python float -> float32, + float32 origin, then (x - scene_origin) / scene_radius."""
+    step = torch.arange(0, up_times, 1)
+    offsets = torch.stack(torch.meshgrid(step, step, step, indexing="ij"), dim=-1).reshape(-1, 3)
+    fine = sparse_ind.repeat_interleave(up_times ** 3, dim=0) * up_times + offsets.repeat([sparse_ind.shape[0], 1])
+    xyz_sfm = fine * voxel_size + vol_origin
     return xyz_sfm, (xyz_sfm - scene_origin) / scene_radius
 
 
 def local_range(n, world_size, rank):
-    per = n // world_size if n % world_size == 0 else n // world_size + 1
+    """Row range of one rank when n rows are zero-padded up to a multiple of world_size and cut evenly:
+    (first row, one past the last REAL row, rows per rank)."""
+    per = -(-n // world_size)
     return rank * per, min(n, (rank + 1) * per), per
