@@ -170,6 +170,7 @@ static int mm_dw(nrw_ctx& c, Planes dY, Planes X, int M, int layer, cudaStream_t
   const int bn = (g.N <= 64) ? 64 : ((g.N <= 128 || c.cur_planes >= 3) ? 128 : 256);
   const int tiles = cdiv(g.M, 128) * cdiv(g.N, bn);
   int ks = 296 / tiles;
+  if (c.backend == NRW_GEMM_TCGEN05 && gemm_tc_wide_dw(g.M, g.N, c.cur_planes)) ks = 74 / (cdiv(g.M, 256) * cdiv(g.N, 512));   // one 256 x 512 tile per CTA pair
   const int max_ks = M / 512 > 0 ? M / 512 : 1;
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;

@@ -29,6 +29,9 @@ inline int gemm(int backend, const GemmDesc& g, cudaStream_t stream) {
 inline int n_products(int n_planes) { return n_planes == 1 ? 1 : (n_planes == 2 ? 3 : 6); }
 
 long long gemm_tc_launch_count();
+// true when gemm_tc runs this split-K weight-gradient shape (M x N output) on 256 x 512 pair tiles: the caller sizes k_slices for
+// one item per CTA pair
+bool gemm_tc_wide_dw(int M, int N, int n_planes);
 // debug: when non-null, every tcgen05 GEMM launch accumulates per-CTA cycle attribution into buf[148*8]
 void gemm_tc_set_profile_buffer(unsigned long long* buf);
 // measurement: CUDA events around every tcgen05 GEMM launch (on the launching stream)

@@ -438,13 +438,21 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 }
 
 // NEW = number of epilogue warps (16, or 8 with more registers per thread and a 3-deep TMA prefetch of the side streams)
-template <int MN_MAJOR, int EK, int NEW>
+// TN  = output columns per pair tile: 256 (two accumulator stages, the epilogue of one tile overlaps the MMAs of the next), or
+//       512 for the split-K weight-gradient GEMMs (MN-major operands, one item per pair): ONE 256 x 512 accumulator filling
+//       the TMEM, two N = 256 MMAs per K step that share the A tile, so a K block costs 48 KB of operand traffic per CTA
+//       instead of 2 x 32 KB.
+template <int MN_MAJOR, int EK, int NEW, int TN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   static_assert(NEW == 16 || NEW == 8, "epilogue warps: 4 or 2 per TMEM lane quarter");
+  static_assert(TN == BN2 || (TN == 2 * BN2 && MN_MAJOR == 1 && EK == EK_GENERIC), "the 512-column tile exists for the weight-gradient GEMMs only");
   constexpr int NBUF = NEW == 8 ? 4 : 2;           // 2 KB staging buffers per epilogue warp (<= 64 KB in total, 32 mbarriers)
+  constexpr int NMMA = TN / BN2;                   // N = 256 MMAs per K step
+  constexpr int NACC = 2 / NMMA;                   // accumulator stages in the 512 TMEM columns
   constexpr int A_TILE = BM * BK * 2;              // this CTA's 128 rows of A
-  constexpr int B_TILE = (BN2 / 2) * BK * 2;       // this CTA's half of B
-  constexpr int TMEM_COLS = 2 * BN2;               // two 256-column accumulators
+  constexpr int B_SUB = (BN2 / 2) * BK * 2;        // this CTA's half of one MMA's B
+  constexpr int B_TILE = NMMA * B_SUB;
+  constexpr int TMEM_COLS = 2 * BN2;               // two 256-column accumulators, or one of 512
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window by OFFSET (an integer round trip of the pointer would turn every staging access
   // into a generic LD/ST instead of LDS/STS)
@@ -516,7 +524,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
       for (int item = unit; item < n_items; item += n_units) {
         const int ks = item % p.k_slices;
         const int t = item / p.k_slices;
-        const int n0 = (t % p.n_tiles) * BN2 + (int)rank * (BN2 / 2);
+        const int n0 = (t % p.n_tiles) * TN + (int)rank * (BN2 / 2);
         const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
         const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -538,7 +546,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                   tma_load_2d_2sm(sa + pl * A_TILE + sl * (64 * BK * 2), &p.tmA[pl], bfl, m0 + 64 * sl, kb * BK);
-                  tma_load_2d_2sm(sb + pl * B_TILE + sl * (64 * BK * 2), &p.tmB[pl], bfl, n0 + 64 * sl, kb * BK);
+#pragma unroll
+                  for (int j = 0; j < NMMA; ++j)      // MMA j covers columns [j * 256, +256) of the tile; this CTA holds its 128 of them
+                    tma_load_2d_2sm(sb + pl * B_TILE + j * B_SUB + sl * (64 * BK * 2), &p.tmB[pl], bfl, n0 + j * BN2 + 64 * sl, kb * BK);
                 }
               }
             }
@@ -595,7 +605,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 if ((p.dbg & 2) && (pr | k)) continue;
-                umma_bf16_2sm(d_tmem, da + ((k * KSTEP) >> 4), db + ((k * KSTEP) >> 4), idesc, accum);
+#pragma unroll
+                for (int j = 0; j < NMMA; ++j)
+                  umma_bf16_2sm(d_tmem + j * BN2, da + ((k * KSTEP) >> 4), db + ((j * B_SUB + k * KSTEP) >> 4), idesc, accum);
                 accum = 1;
               }
             }
@@ -606,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
         }
         if (issuer) umma_commit_2sm(bar_tfull + 8 * acc);
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_ph ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 4 + NEW) {
@@ -618,7 +630,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
     float* stg = reinterpret_cast<float*>(smem + STAGE_BUDGET + BAR_BYTES) + ew * 512;
     int acc = 0;
     uint32_t acc_ph = 0;
-    const bool use_cs = p.epi.colsum != nullptr && !p.epi.atomic;
+    const bool use_cs = TN == BN2 && p.epi.colsum != nullptr && !p.epi.atomic;
     const int etid = threadIdx.x - 128;
     int cs_n0 = -1;   // n-tile the shared column-sum accumulator currently holds
     // ---- side-stream staging: this warp's NBUF 2 KB slots + their mbarriers; a [32 x 16] bf16 TMA box per stream and
@@ -656,7 +668,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item % p.k_slices;
       const int t = item / p.k_slices;
-      const int n0 = (t % p.n_tiles) * BN2;
+      const int n0 = (t % p.n_tiles) * TN;
       const int m0 = (t / p.n_tiles) * (2 * BM) + (int)rank * BM;
       const int kb0 = ks * kb_per, kb1 = min(kb_total, kb0 + kb_per);
       if (use_cs && n0 != cs_n0) {
@@ -674,7 +686,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
       if (prof) atomicAdd(&p.prof[blockIdx.x * 16 + 6], 1ull);
       float hacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // FWD_HEAD: this lane's rows of the fused SDF-head dot product
       if (kb1 > kb0) {
-        for (int c = chalf; c < BN2 / 16; c += CH_PER) {
+        for (int c = chalf; c < TN / 16; c += CH_PER) {
           const int nc = n0 + c * 16;
           if (nc >= p.N) break;
           const int m0w = m0 + quarter * 32;
@@ -706,7 +718,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
       __syncwarp();
       NRW_PROF_ADD(prof, 4);
       if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == NACC) { acc = 0; acc_ph ^= 1; }
     }
     if (use_cs && cs_n0 >= 0) colsum_flush(cs_buf, p.epi.colsum, cs_n0, min(min(p.N, p.epi.n_store) - cs_n0, BN2), etid, 32 * NEW, 1);
   }
@@ -816,15 +828,23 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   return NRW_OK;
 }
 
-template <int MN, int EK, int NEW = N_EPI_WARPS>
+template <int MN, int EK, int NEW = N_EPI_WARPS, int TN = 256>
 static int launch2(const TcParams& p, int pairs, int dev, cudaStream_t stream) {
   static bool attr_set[MAX_DEV] = {false};
   if (!attr_set[dev]) {
-    NRW_CUDA_OK((cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    NRW_CUDA_OK((cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK, NEW, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     attr_set[dev] = true;
   }
-  gemm_tc2_kernel<MN, EK, NEW><<<2 * pairs, 128 + 32 * NEW, SMEM_BYTES, stream>>>(p);
+  gemm_tc2_kernel<MN, EK, NEW, TN><<<2 * pairs, 128 + 32 * NEW, SMEM_BYTES, stream>>>(p);
   return NRW_OK;
+}
+
+// 512-column pair tiles for the split-K weight-gradient GEMMs (see gemm_tc2_kernel).  NRW_DW_WIDE: 0 off, 1 one-plane
+// operands only (default: two planes leave 2 TMA stages of 96 KB), 2 always.
+bool gemm_tc_wide_dw(int M, int N, int n_planes) {
+  static const int mode = getenv("NRW_DW_WIDE") ? atoi(getenv("NRW_DW_WIDE")) : 1;
+  static const int use_2cta = getenv("NRW_TC_2CTA") ? atoi(getenv("NRW_TC_2CTA")) : 1;
+  return use_2cta && mode > 0 && M >= 256 && N >= 2 * BN2 && n_planes <= (mode >= 2 ? 2 : 1);
 }
 
 static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream);
@@ -910,7 +930,8 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) for the wide layers
   static const int use_2cta = getenv("NRW_TC_2CTA") ? atoi(getenv("NRW_TC_2CTA")) : 1;
   if (use_2cta && g.N >= 256 && g.M >= 256) {
-    p.m_tiles = cdiv(g.M, 2 * BM); p.n_tiles = cdiv(g.N, BN2);
+    const bool wide = g.mn_major && g.epi.atomic && gemm_tc_wide_dw(g.M, g.N, g.n_planes);
+    p.m_tiles = cdiv(g.M, 2 * BM); p.n_tiles = cdiv(g.N, wide ? 2 * BN2 : BN2);
     for (int pl = 0; pl < g.n_planes; ++pl) {
       if (!g.mn_major) {
         NRW_CHECK(g.K % BK == 0, NRW_ERR_ARG, "gemm_tc: K=%d must be a multiple of %d (pad the operand)", g.K, BK);
@@ -945,7 +966,8 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
         p.aux_stage = mask;
       }
     }
-    if (g.mn_major) { NRW_TRY((launch2<1, EK_GENERIC>(p, pairs, dev, stream))); }
+    if (g.mn_major && wide) { NRW_TRY((launch2<1, EK_GENERIC, N_EPI_WARPS, 2 * BN2>(p, pairs, dev, stream))); }
+    else if (g.mn_major) { NRW_TRY((launch2<1, EK_GENERIC>(p, pairs, dev, stream))); }
     else {
       switch (ek) {
         case EK_FWD_SOFTPLUS: NRW_TRY((launch2<0, EK_FWD_SOFTPLUS>(p, pairs, dev, stream))); break;
