@@ -503,10 +503,30 @@ def main():
     # ---- roofline of the dominant kernel: CUDA events around EVERY tcgen05 GEMM launch of two more steps.
     # Every rank runs them (the step holds the gradient all-reduce); only rank 0's kernel times are reported. ----
     L.nrw_gemm_timing(1, None)
+    sysm.stage_events = []
     run(2, False)
     torch.cuda.synchronize()
     out5 = (C.c_double * 5)()
     L.nrw_gemm_timing(0, out5)
+    # ---- where the step goes, per rank (CUDA events TrainSystem records in-stream at its stage boundaries, same two steps):
+    # compute = forward + backward up to the all-reduce; reduce = the two NCCL all-reduces INCLUDING the wait for the slowest rank
+    # (so min over ranks = the collective itself, and max over ranks of compute = what weak scaling is bounded by). ----
+    ev, sysm.stage_events = sysm.stage_events, None
+    acc = {}
+    for (n0, a0), (n1, a1) in zip(ev, ev[1:]):
+        if n1 != "start":
+            acc[n1] = acc.get(n1, 0.0) + a0.elapsed_time(a1) / 2
+    st = torch.tensor([acc.get("forward", 0.0) + acc.get("backward", 0.0), acc.get("reduce", 0.0), acc.get("optimizer", 0.0)],
+                      device=device, dtype=torch.float64)
+    st_all = [torch.zeros_like(st) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(st_all, st)
+    else:
+        st_all = [st]
+    stages = {"compute_ms_per_rank": [round(float(x[0]), 3) for x in st_all], "reduce_ms_per_rank": [round(float(x[1]), 3) for x in st_all],
+              "optimizer_ms_per_rank": [round(float(x[2]), 3) for x in st_all],
+              "note": "2 steps after the timed region with per-launch GEMM events on; reduce includes waiting for the slowest rank "
+                      "(min over ranks = the NCCL all-reduces themselves)"}
     trace_share = None
     if fine and rank == 0:      # share of the step spent tracing the SDF-derived octree (K1a)
         r = sysm.renderer
@@ -535,6 +555,7 @@ def main():
             "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "clocks": clk2},
             "roofline": roofline_from_timing(L, out5, 2, ms, flops_step, peak_tf, peak_src)}
+    line["stages"] = stages
     if trace_share:
         line["octree_trace"] = trace_share
     if world == 1:

@@ -194,6 +194,7 @@ class TrainSystem:
         self._mark("start")
         loss, flat, eg = self.compute_grads(batch)
         self.reduce_grads(flat, eg)
+        self._mark("reduce")
         self.apply_grads(flat, eg)
         return loss
 
