@@ -133,6 +133,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// Programmatic dependent launch: a GEMM launched with the stream-serialisation attribute may have its CTAs scheduled while the
+// previous kernel of the stream drains (each SM takes the next kernel's CTA as soon as its own finishes), so barrier init, TMEM
+// allocation and descriptor prefetch overlap the predecessor's tail.  pdl_wait() returns once the predecessor has completed and
+// its writes are visible: nothing before it may touch global memory.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // one lane of the (converged) warp, the same one every time
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -225,6 +231,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.k_slices - 1) / p.k_slices;
@@ -505,6 +513,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1) g
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.k_slices - 1) / p.k_slices;
@@ -812,6 +822,26 @@ static int current_device() {
   return (dev >= 0 && dev < MAX_DEV) ? dev : 0;
 }
 
+// every tcgen05 GEMM goes through here.  NRW_PDL (default 1; 0 = plain launches): programmatic dependent launch (see pdl_wait); consecutive GEMMs of a layer
+// chain then overlap their prologues with the predecessor's tail.  Other kernels of the stream are launched normally and
+// serialise as usual.
+template <typename Kernel>
+static cudaError_t launch_gemm(Kernel kernel, int grid, int block, cudaStream_t stream, const TcParams& p) {
+  static const int pdl = getenv("NRW_PDL") ? atoi(getenv("NRW_PDL")) : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 template <int BN, int MN>
 static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   static bool attr_set[MAX_DEV] = {false};
@@ -822,7 +852,7 @@ static int launch(const TcParams& p, int n_sm, cudaStream_t stream) {
   }
   const int items = p.m_tiles * p.n_tiles * p.k_slices;
   const int grid = items < n_sm ? items : n_sm;
-  gemm_tc_kernel<BN, MN><<<grid, N_THREADS, SMEM_BYTES, stream>>>(p);
+  NRW_CUDA_OK(launch_gemm(gemm_tc_kernel<BN, MN>, grid, N_THREADS, stream, p));
   NRW_LAUNCH_OK();
   ++g_tc_launches;
   return NRW_OK;
@@ -835,7 +865,7 @@ static int launch2(const TcParams& p, int pairs, int dev, cudaStream_t stream) {
     NRW_CUDA_OK((cudaFuncSetAttribute(gemm_tc2_kernel<MN, EK, NEW, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     attr_set[dev] = true;
   }
-  gemm_tc2_kernel<MN, EK, NEW, TN><<<2 * pairs, 128 + 32 * NEW, SMEM_BYTES, stream>>>(p);
+  NRW_CUDA_OK((launch_gemm(gemm_tc2_kernel<MN, EK, NEW, TN>, 2 * pairs, 128 + 32 * NEW, stream, p)));
   return NRW_OK;
 }
 
@@ -929,7 +959,10 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   p.dbg = dbg;
   // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles) for the wide layers
   static const int use_2cta = getenv("NRW_TC_2CTA") ? atoi(getenv("NRW_TC_2CTA")) : 1;
-  if (use_2cta && g.N >= 256 && g.M >= 256) {
+  // NRW_PAIR_MIN_N: narrowest K-major layer that takes the CTA-pair kernel and its specialised epilogues (a 128-wide layer fills half
+  // of the 256-column pair tile: the second CTA's half of B is out of range and arrives as zeros)
+  static const int pair_min_n = getenv("NRW_PAIR_MIN_N") ? atoi(getenv("NRW_PAIR_MIN_N")) : 128;
+  if (use_2cta && g.M >= 256 && g.N >= (g.mn_major ? 256 : pair_min_n)) {
     const bool wide = g.mn_major && g.epi.atomic && gemm_tc_wide_dw(g.M, g.N, g.n_planes);
     p.m_tiles = cdiv(g.M, 2 * BM); p.n_tiles = cdiv(g.N, wide ? 2 * BN2 : BN2);
     for (int pl = 0; pl < g.n_planes; ++pl) {
