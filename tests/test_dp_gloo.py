@@ -1,5 +1,6 @@
 """CPU, world_size 2 over gloo: the data-parallel reduction logic of nrw/train.py - every .grad is a view of ONE flat
-buffer, a single all-reduce averages all of them, per-rank loss normalisers stay per-rank."""
+buffer, a single all-reduce averages all of them, per-rank loss normalisers stay per-rank; TrainSystem.reduce_grads itself on the same
+buffers; disjoint ray-cache shards per rank."""
 import os
 import socket
 
@@ -44,6 +45,27 @@ def _worker(rank, world, port, q):
     for _, _, off, numel in table:
         used[off:off + numel] = True
     ok &= bool(torch.all(flat_grad[~used] == 0))
+    # the product's own reduction (nrw/train.py::TrainSystem.reduce_grads, the world_size > 1 branch of training_step) on the
+    # same buffers: DDP mean of the flat gradient and of the dense embedding gradient, in place
+    import types
+
+    from nrw.raycache import local_split
+    from nrw.train import TrainSystem
+
+    for i, (name, p, off, numel) in enumerate(params):
+        p.grad.fill_(float(rank + 1) * (i + 1))
+    emb_grad = torch.full((100, 48), float(10 * (rank + 1)))
+    ptr = flat_grad.data_ptr()
+    TrainSystem.reduce_grads(types.SimpleNamespace(world_size=world), flat_grad, emb_grad)
+    ok &= flat_grad.data_ptr() == ptr and bool(torch.all(emb_grad == 10.0 * sum(r + 1 for r in range(world)) / world))
+    for i, (name, p, off, numel) in enumerate(params):
+        ok &= bool(torch.all(p.grad == (i + 1) * sum(r + 1 for r in range(world)) / world))
+    # ray-cache shards: every rank derives the same permutation and takes a disjoint slice (datasets/data.py:83-100)
+    mine = local_split([f"split_{i}" for i in range(64)], world, rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    flat_names = [n for part in gathered for n in part]
+    ok &= len(flat_names) == 64 and len(set(flat_names)) == 64 and all(len(part) == 64 // world for part in gathered)
     q.put((rank, ok))
     dist.destroy_process_group()
 
