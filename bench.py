@@ -58,7 +58,7 @@ class ClockSampler:
     BITS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.sm, self.mx, self.reasons = index, [], [], set()
+        self.index, self.sm, self.mx, self.reasons, self.power = index, [], [], set(), []
         self.stop_flag, self.thread, self.proc, self.source = threading.Event(), None, None, None
 
     def _nvml_loop(self, nv, h):
@@ -66,6 +66,10 @@ class ClockSampler:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)      # board power, W
+                except Exception:
+                    pass
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 for name, bit in self.BITS:
                     if r & bit:
@@ -119,9 +123,12 @@ class ClockSampler:
         if self.proc is not None:
             self.proc.terminate()
         self.thread.join(timeout=2.0)
-        sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
+        sm, pw = sorted(self.sm), sorted(self.power)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+               "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
+        if pw:
+            out["power_w"] = {"median": pw[len(pw) // 2], "max": pw[-1]}
+        return out
 
 
 def peaks():
@@ -538,6 +545,7 @@ def main():
             r.get_near_far_sdf(r.fine_octree_data, ro, rays[:, 3:6].contiguous(), rays[:, 6:7] / r.radius, rays[:, 7:8] / r.radius)
         e1.record(); torch.cuda.synchronize()
         trace_share = {"octree_trace_ms_per_step": e0.elapsed_time(e1) / 20, "share_of_step": e0.elapsed_time(e1) / 20 / ms}
+        r = rays = ro = None        # do not keep the first system (and its activation slots) alive through these locals
     barrier()
     if rank != 0:
         if world > 1:
