@@ -209,6 +209,16 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
   // the last layer - u_8 is never written, the head kernel never reads it (CTA-pair tcgen05 kernel only: M >= 256)
   static const int no_fused_head = getenv("NRW_FUSED_HEAD") ? !atoi(getenv("NRW_FUSED_HEAD")) : 0;
   const bool fused_head = !need_normal && !need_feat && M >= 256 && c.backend == NRW_GEMM_TCGEN05 && !no_fused_head;
+  // NRW_SDF_FUSED=1: the whole forward-only chain (encoding, 8 layers, head) as ONE kernel with the activations resident in
+  // shared memory (gemm_tc.cu::sdf_fused_kernel) - two-plane operands only
+  static const int fused_chain = getenv("NRW_SDF_FUSED") ? atoi(getenv("NRW_SDF_FUSED")) : 0;
+  if (fused_head && fused_chain && P == 2) {
+    SdfFusedDesc d;
+    d.pts = pts; d.sdf = c.c_sdf; d.M = M;
+    for (int l = 0; l < 8; ++l) { d.W[l] = c.W(L_SDF0 + l); d.bias[l] = c.bias(L_SDF0 + l); }
+    d.head_w = w0; d.head_b = b0;
+    return sdf_fused_forward(d, s);
+  }
   for (int l = 0; l < 8; ++l) {
     Epi e;
     e.bias = c.bias(L_SDF0 + l);

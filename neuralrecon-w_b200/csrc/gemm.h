@@ -28,6 +28,19 @@ inline int gemm(int backend, const GemmDesc& g, cudaStream_t stream) {
 // number of (a_plane, b_plane) products issued for a given plane count: 1, 3, 6
 inline int n_products(int n_planes) { return n_planes == 1 ? 1 : (n_planes == 2 ? 3 : 6); }
 
+// Fused forward-only SDF chain (gemm_tc.cu::sdf_fused_kernel): points -> sdf, activations resident in shared memory.
+// W[l] = packed K-major weights of SDF layer l ([512 x Kp] bf16, two planes), bias[l] fp32 [512]; head_w / head_b = lin8 row 0.
+struct SdfFusedDesc {
+  const float* pts = nullptr;   // [M, 3]
+  float* sdf = nullptr;         // [M]
+  int M = 0;
+  Planes W[8];
+  const float* bias[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const float* head_w = nullptr;
+  const float* head_b = nullptr;
+};
+int sdf_fused_forward(const SdfFusedDesc& d, cudaStream_t stream);
+
 long long gemm_tc_launch_count();
 // true when gemm_tc runs this split-K weight-gradient shape (M x N output) on 256 x 512 pair tiles: the caller sizes k_slices for
 // one item per CTA pair

@@ -1048,4 +1048,366 @@ static int gemm_tc_impl(const GemmDesc& g, cudaStream_t stream) {
   }
 }
 
+
+// =======================================================================================
+// Fused forward-only SDF chain (sampler queries, NeuconWRenderer.sdf, the 512^3 grid of config 5):
+//   positional encoding -> 8 x (512-wide layer, bias, softplus, [skip concat]) -> sdf head, ONE persistent kernel.
+//   models/neuconw.py:263-279 (SDFNetwork.forward) + :281-282 (sdf): the reference runs 9 Linear + 8 Softplus + cat per chunk.
+//
+//   A CTA pair owns 128 sample rows, 64 per CTA (tcgen05.mma.cta_group::2 with M = 128: each SM feeds 64 rows and half of the
+//   256 weight rows of an MMA; 64 rows x 256 columns of fp32 land in 128 lanes x 128 columns of its TMEM).  The two bf16 planes
+//   of the 64 x 512 activation tile live in shared memory (128 KB) in exactly the K-major 128B-swizzled layout the next layer's
+//   MMAs read; the weights stream from L2 through a 3-stage TMA ring (one stage = one 64-wide k-block of one 256-column half,
+//   both planes: 32 KB per CTA); accumulators ping-pong between the two halves of the TMEM by layer parity.  HBM sees 12 bytes
+//   per sample in and 4 bytes out.
+//
+//   Within a layer the MMAs are issued as  h0[kb 0-3], h1[kb 0-3], h0[kb 4-7] -> commit, h1[kb 4-7] -> commit  (h = column half
+//   of the output): once half 0 is committed every read of input k-blocks 0-3 has completed, so the epilogue of half 0 may
+//   overwrite them IN PLACE with the new activations (columns 0-255 of the output = k-blocks 0-3 of the next layer) while the
+//   tensor pipe still works on half 1; the next layer starts on k-blocks 0-3 as soon as they are written (a_ready[0]) and on
+//   k-blocks 4-7 after the epilogue of half 1 (a_ready[1]).  Same product order and k order per output element as the
+//   per-layer kernels above, so the activations are bit-identical to the unfused chain.
+// =======================================================================================
+static constexpr int FZ_ROWS = 64;                         // rows per CTA
+static constexpr int FZ_APLANE = FZ_ROWS * 512 * 2;        // one bf16 plane of the activation tile: 8 k-blocks of [64 x 64]
+static constexpr int FZ_A = 2 * FZ_APLANE;
+static constexpr int FZ_WPL = 128 * BK * 2;                // this CTA's 128 weight rows of one k-block, one plane
+static constexpr int FZ_WSTAGE = 2 * FZ_WPL;
+static constexpr int FZ_NST = 3;
+static constexpr int FZ_BAR = FZ_A + FZ_NST * FZ_WSTAGE;
+static constexpr int FZ_SMEM = 1024 + FZ_BAR + 256;
+static constexpr int FZ_PART = 2 * 8192;                   // head partials [64 rows][16 slots] fp32 in k-block 2 of plane 0 (free by then)
+static_assert(FZ_SMEM <= 232448, "dynamic shared memory limit of sm_100");
+
+struct SdfFusedParams {
+  CUtensorMap tmW[8][2];     // layer l, plane p: [512 n-rows] x [Kp] bf16, box {64 k, 128 n}, 128B swizzle
+  const float* bias[8];
+  const float* head_w;       // lin8 row 0 (512)
+  const float* head_b;       // its bias
+  const float* pts;          // [M, 3]
+  float* sdf;                // [M]
+  int M, n_tiles;            // n_tiles counts 128-row pair tiles
+};
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the peer CTA's writes
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAITC_DONE;\n"
+      "bra.uni WAITC_LOOP;\n"
+      "WAITC_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps of this CTA
+
+// feature f (0..38) of the 6-frequency positional encoding of x[3]: [x, sin(2^k x), cos(2^k x)]_k, as csrc/embed.cu lays it out
+__device__ __forceinline__ float pe6_feature(const float (&x)[3], int f) {
+  if (f < 3) return x[f];
+  const int k = (f - 3) / 6, wi = (f - 3) % 6, c = wi % 3;
+  float sn, cs;
+  sincosf(x[c] * (float)(1 << k), &sn, &cs);
+  return wi < 3 ? sn : cs;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_kernel(const __grid_constant__ SdfFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FZ_BAR);
+  const uint32_t w_full = smem_u32(bars), w_empty = smem_u32(bars + 3), acc_full = smem_u32(bars + 6), a_ready = smem_u32(bars + 8);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < 8; ++l) { tma_prefetch_desc(&p.tmW[l][0]); tma_prefetch_desc(&p.tmW[l][1]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < FZ_NST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(a_ready + 8 * i, 32); }   // 16 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int unit = blockIdx.x >> 1, n_units = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== weight producer (both CTAs: each streams its 128 of the 256 weight rows of an MMA) =====================
+    const bool issuer = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = unit; tile < p.n_tiles; tile += n_units) {
+      for (int l = 0; l < 8; ++l) {
+        const int nu = l == 0 ? 2 : 16;
+        for (int u = 0; u < nu; ++u) {
+          const int g = u >> 2;
+          const int h = l == 0 ? u : (g & 1), kb = l == 0 ? 0 : ((g >> 1) * 4 + (u & 3));
+          mbar_wait(w_empty + 8 * s, ph ^ 1);
+          if (issuer) {
+            if (leader) mbar_arrive_expect_tx(w_full + 8 * s, 2 * FZ_WSTAGE);
+            const uint32_t bfl = (w_full + 8 * s) & PEER_MASK;
+            const uint32_t dst = smem0 + FZ_A + s * FZ_WSTAGE;
+            const int n0 = h * 256 + (int)rank * 128;
+            tma_load_2d_2sm(dst, &p.tmW[l][0], bfl, kb * BK, n0);
+            tma_load_2d_2sm(dst + FZ_WPL, &p.tmW[l][1], bfl, kb * BK, n0);
+          }
+          __syncwarp();
+          if (++s == FZ_NST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (leader) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t desc_hi = make_sdesc(0, 16, 1024);
+      const bool issuer = elect_one();
+      int s = 0;
+      uint32_t ph = 0, pa0 = 0, pa1 = 0;
+      for (int tile = unit; tile < p.n_tiles; tile += n_units) {
+        for (int l = 0; l < 8; ++l) {
+          const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
+          mbar_wait_cluster(a_ready, pa0);       // input k-blocks 0-3 (layer 0: the encoded points) are in shared memory
+          pa0 ^= 1;
+          tc_fence_after();
+          const int nu = l == 0 ? 2 : 16;
+          for (int u = 0; u < nu; ++u) {
+            const int g = u >> 2;
+            const int h = l == 0 ? u : (g & 1), kb = l == 0 ? 0 : ((g >> 1) * 4 + (u & 3));
+            if (l > 0 && u == 8) {               // input k-blocks 4-7
+              mbar_wait_cluster(a_ready + 8, pa1);
+              pa1 ^= 1;
+              tc_fence_after();
+            }
+            mbar_wait(w_full + 8 * s, ph);
+            tc_fence_after();
+            if (issuer) {
+              const uint32_t sa = smem0 + kb * (FZ_ROWS * BK * 2);
+              const uint32_t sb = smem0 + FZ_A + s * FZ_WSTAGE;
+              uint32_t accum = kb != 0;
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr) {   // (hi, lo), (lo, hi), (hi, hi): the product order of the per-layer kernels
+                const uint32_t pa = pr == 1 ? 1u : 0u, pb = pr == 0 ? 1u : 0u;
+                const uint64_t da = desc_hi | (uint64_t)(((sa + pa * FZ_APLANE) & 0x3FFFFu) >> 4);
+                const uint64_t db = desc_hi | (uint64_t)(((sb + pb * FZ_WPL) & 0x3FFFFu) >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  umma_bf16_2sm(acc + (uint32_t)h * 128u, da + ((k * 32) >> 4), db + ((k * 32) >> 4), idesc, accum);
+                  accum = 1;
+                }
+              }
+              umma_commit_2sm(w_empty + 8 * s);
+              if (l == 0 || u == 11 || u == 15) umma_commit_2sm(acc_full + 8 * h);
+            }
+            __syncwarp();
+            if (++s == FZ_NST) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 64 rows) =====================
+    const int ew = warp - 4, q = warp & 3, chalf = ew >> 2, et = threadIdx.x - 128;
+    const int row = 32 * (q & 1) + lane;                       // TMEM lanes 0-63: columns 0-127 of the MMA, lanes 64-127: columns 128-255
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int colq = 128 * (q >> 1);
+    const int rsw = row & 7;
+    float* part = reinterpret_cast<float*>(smem + FZ_PART);
+    uint32_t pacc = 0;
+    for (int tile = unit; tile < p.n_tiles; tile += n_units) {
+      const int m0 = tile * 128 + (int)rank * FZ_ROWS;
+      // ---- layer-0 input: positional encoding of this CTA's 64 points, written as the k-block-0 tiles of both planes ----
+      *reinterpret_cast<uint4*>(smem + et * 16) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem + FZ_APLANE + et * 16) = make_uint4(0, 0, 0, 0);
+      epi_bar_sync();
+      if (et < 3 * FZ_ROWS) {
+        const int r = et / 3, c = et % 3, m = m0 + r;
+        const float x = m < p.M ? __ldg(p.pts + (long long)m * 3 + c) : 0.0f;
+        auto put = [&](int j, float v) {
+          const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+          const int off = r * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+          *reinterpret_cast<bf16*>(smem + off) = hi;
+          *reinterpret_cast<bf16*>(smem + FZ_APLANE + off) = lo;
+        };
+        put(c, x);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          float sn, cs;
+          sincosf(x * (float)(1 << k), &sn, &cs);
+          put(3 + 6 * k + c, sn);
+          put(3 + 6 * k + 3 + c, cs);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();                       // the head epilogue of the previous tile has drained its accumulators
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader_release(a_ready);
+      const int mrow = m0 + row;
+      for (int l = 0; l < 8; ++l) {
+        const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
+        const float* bias = p.bias[l];
+        const float scale = l == 3 ? 0.70710678118654752440f : 1.0f;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(acc_full + 8 * h, pacc);
+          tc_fence_after();
+          float hsum = 0.0f;
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = chalf + 4 * cc;
+            const int n = 256 * h + colq + 16 * c;             // first of this thread's 16 output columns
+            float v[16];
+            tmem_ld16(acc + (uint32_t)(h * 128 + 16 * c) + lane_sel, v);
+            float b[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
+              b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+            }
+            if (l == 7) {                                      // sdf head: fixed-order partial dot product with lin8's row 0
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 hw = __ldg(reinterpret_cast<const float4*>(p.head_w + n) + i);
+                hsum = fmaf(softplus100(v[4 * i] + b[4 * i]), hw.x, hsum);
+                hsum = fmaf(softplus100(v[4 * i + 1] + b[4 * i + 1]), hw.y, hsum);
+                hsum = fmaf(softplus100(v[4 * i + 2] + b[4 * i + 2]), hw.z, hsum);
+                hsum = fmaf(softplus100(v[4 * i + 3] + b[4 * i + 3]), hw.w, hsum);
+              }
+              continue;
+            }
+            float w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = softplus100(v[i] + b[i]) * scale;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
+              const float2 hf = __bfloat1622float2(hh);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(w[2 * i] - hf.x, w[2 * i + 1] - hf.y);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            uint8_t* dst = smem + (n >> 6) * (FZ_ROWS * BK * 2) + row * 128;
+            const int ch0 = (n & 63) >> 3;
+            const int o0 = ((ch0 ^ rsw) << 4), o1 = (((ch0 + 1) ^ rsw) << 4);
+            *reinterpret_cast<uint4*>(dst + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(dst + FZ_APLANE + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(dst + FZ_APLANE + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            if (l == 3 && n + 15 >= 473) {                     // skip connection: columns 473-511 of layer 4's input = PE(x) / sqrt(2)
+              float x[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) x[i] = mrow < p.M ? __ldg(p.pts + (long long)mrow * 3 + i) : 0.0f;
+#pragma unroll 1
+              for (int i = n < 473 ? 473 - n : 0; i < 16; ++i) {       // overwrites what the same thread stored above
+                const float pv = pe6_feature(x, n + i - 473) * 0.70710678118654752440f;
+                const bf16 ph = __float2bfloat16_rn(pv), pl = __float2bfloat16_rn(pv - __bfloat162float(ph));
+                const int off = ((((ch0 + (i >> 3)) ^ rsw)) << 4) + (i & 7) * 2;
+                *reinterpret_cast<bf16*>(dst + off) = ph;
+                *reinterpret_cast<bf16*>(dst + FZ_APLANE + off) = pl;
+              }
+            }
+          }
+          if (l == 7) {
+            part[row * 16 + h * 8 + (q >> 1) * 4 + chalf] = hsum;
+          } else {
+            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(a_ready + 8 * h);
+          }
+        }
+        pacc ^= 1;
+      }
+      // ---- sdf = sum of the 16 column partials in a fixed order + bias ----
+      epi_bar_sync();
+      if (et < FZ_ROWS) {
+        const float4* pr4 = reinterpret_cast<const float4*>(part + et * 16);
+        const float4 a = pr4[0], b4 = pr4[1], c4 = pr4[2], d4 = pr4[3];
+        const float sum = (((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w))) + (((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w)));
+        const int m = m0 + et;
+        if (m < p.M) p.sdf[m] = sum + __ldg(p.head_b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int sdf_fused_forward(const SdfFusedDesc& d, cudaStream_t stream) {
+  NRW_CHECK(d.M > 0 && d.pts && d.sdf && d.head_w && d.head_b, NRW_ERR_ARG, "sdf_fused_forward: bad arguments (M=%d)", d.M);
+  SdfFusedParams p;
+  memset(&p, 0, sizeof(p));
+  for (int l = 0; l < 8; ++l) {
+    const int K = l == 0 ? 64 : 512;
+    NRW_CHECK(d.W[l].p && d.W[l].ld == K && d.bias[l], NRW_ERR_ARG, "sdf_fused_forward: layer %d needs packed [512 x %d] weights (ld=%d)", l, K, d.W[l].ld);
+    for (int pl = 0; pl < 2; ++pl) NRW_TRY(make_map(&p.tmW[l][pl], d.W[l].plane(pl), K, 512, d.W[l].ld, BK, 128));
+    p.bias[l] = d.bias[l];
+  }
+  p.head_w = d.head_w; p.head_b = d.head_b; p.pts = d.pts; p.sdf = d.sdf; p.M = d.M;
+  p.n_tiles = cdiv(d.M, 2 * FZ_ROWS);
+  static int n_sm_dev[MAX_DEV] = {0};
+  static bool attr_set[MAX_DEV] = {false};
+  const int dev = current_device();
+  if (!n_sm_dev[dev]) NRW_CUDA_OK(cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  if (!attr_set[dev]) {
+    NRW_CUDA_OK(cudaFuncSetAttribute(sdf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+    attr_set[dev] = true;
+  }
+  int pairs = n_sm_dev[dev] / 2;
+  if (p.n_tiles < pairs) pairs = p.n_tiles;
+  static const int pdl = getenv("NRW_PDL") ? atoi(getenv("NRW_PDL")) : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(640, 1, 1);
+  cfg.dynamicSmemBytes = FZ_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TimedLaunch L;
+  if (g_timing_on) {   // bench.py roofline: this launch replaces the 8 per-layer GEMMs of a forward-only chunk
+    L.e0 = get_event(); L.e1 = get_event();
+    L.flops = 2.0 * d.M * 512.0 * (64.0 + 7.0 * 512.0);
+    L.mma_flops = 3.0 * L.flops;
+    L.M = d.M; L.N = 512; L.K = 64 + 7 * 512; L.P = 2; L.mn = 0; L.ks = 1; L.epi = 4096u;
+    L.bytes = 16.0 * d.M;
+    NRW_CUDA_OK(cudaEventRecord(L.e0, stream));
+  }
+  NRW_CUDA_OK(cudaLaunchKernelEx(&cfg, sdf_fused_kernel, p));
+  if (g_timing_on) {
+    NRW_CUDA_OK(cudaEventRecord(L.e1, stream));
+    g_timed.push_back(L);
+  }
+  NRW_LAUNCH_OK();
+  ++g_tc_launches;
+  return NRW_OK;
+}
+
 }  // namespace nrw
