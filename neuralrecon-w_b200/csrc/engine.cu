@@ -199,6 +199,21 @@ static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld,
 // ---------------------------------------------------------------------------------------------
 // forward chunks
 // ---------------------------------------------------------------------------------------------
+// NRW_SDF_FUSED=1: a forward-only chain (encoding, 8 layers, head) runs as ONE kernel with the activations resident in shared
+// memory (gemm_tc.cu::sdf_fused_kernel); two-plane operands on the tcgen05 backend only.  It needs no chunk workspace.
+static bool sdf_fused_enabled(const nrw_ctx& c) {
+  static const int fused_chain = getenv("NRW_SDF_FUSED") ? atoi(getenv("NRW_SDF_FUSED")) : 0;
+  return fused_chain && c.backend == NRW_GEMM_TCGEN05 && c.n_planes == 2;
+}
+static int sdf_fused_query(nrw_ctx& c, const float* pts, int M, float* sdf, cudaStream_t s) {
+  SdfFusedDesc d;
+  d.pts = pts; d.sdf = sdf; d.M = M;
+  for (int l = 0; l < 8; ++l) { d.W[l] = c.W(L_SDF0 + l); d.bias[l] = c.bias(L_SDF0 + l); }
+  d.head_w = c.f_area + c.pm.heads.sdf_w0;
+  d.head_b = c.f_area + c.pm.heads.sdf_b0;
+  return sdf_fused_forward(d, s);
+}
+
 int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, bool need_feat, cudaStream_t s) {
   c.cur_planes = c.n_planes;
   const int P = c.n_planes;
@@ -211,14 +226,7 @@ int sdf_chunk_forward(nrw_ctx& c, int M, const float* pts, bool need_normal, boo
   const bool fused_head = !need_normal && !need_feat && M >= 256 && c.backend == NRW_GEMM_TCGEN05 && !no_fused_head;
   // NRW_SDF_FUSED=1: the whole forward-only chain (encoding, 8 layers, head) as ONE kernel with the activations resident in
   // shared memory (gemm_tc.cu::sdf_fused_kernel) - two-plane operands only
-  static const int fused_chain = getenv("NRW_SDF_FUSED") ? atoi(getenv("NRW_SDF_FUSED")) : 0;
-  if (fused_head && fused_chain && P == 2) {
-    SdfFusedDesc d;
-    d.pts = pts; d.sdf = c.c_sdf; d.M = M;
-    for (int l = 0; l < 8; ++l) { d.W[l] = c.W(L_SDF0 + l); d.bias[l] = c.bias(L_SDF0 + l); }
-    d.head_w = w0; d.head_b = b0;
-    return sdf_fused_forward(d, s);
-  }
+  if (fused_head && sdf_fused_enabled(c)) return sdf_fused_query(c, pts, M, c.c_sdf, s);
   for (int l = 0; l < 8; ++l) {
     Epi e;
     e.bias = c.bias(L_SDF0 + l);
@@ -455,6 +463,12 @@ int nerf_chunk_backward(nrw_ctx& c, int M, const float* d_bga, const float* d_bg
 // public operations
 // ---------------------------------------------------------------------------------------------
 int sdf_query(nrw_ctx& c, const float* pts, long long n, float* sdf, cudaStream_t s) {
+  if (sdf_fused_enabled(c) && n > 0) {            // no workspace, no chunking (the forward cache of a training render stays valid)
+    const long long step = 1ll << 28;
+    for (long long i = 0; i < n; i += step)
+      NRW_TRY(sdf_fused_query(c, pts + i * 3, (int)((n - i) < step ? (n - i) : step), sdf + i, s));
+    return NRW_OK;
+  }
   c.fwd_cached = false;  // slot 0 is about to be overwritten
   c.use_sdf_slot(0);
   for (long long i = 0; i < n; i += c.Mc) {

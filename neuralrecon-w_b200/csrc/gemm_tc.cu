@@ -1089,22 +1089,9 @@ struct SdfFusedParams {
   int M, n_tiles;            // n_tiles counts 128-row pair tiles
 };
 
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the peer CTA's writes
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAITC_DONE;\n"
-      "bra.uni WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
-}
+// (Barrier waits / remote arrivals keep the default CTA-scope semantics of the kernels above: the activations live in shared
+//  memory and are read by the tensor core through the async proxy - fence.proxy.async on the writer side - so no L1 is involved;
+//  a cluster-scope acquire compiled to CCTL.IVALL on every a_ready wait and threw the biases out of L1: ncu, first version.)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps of this CTA
 
@@ -1186,7 +1173,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       for (int tile = unit; tile < p.n_tiles; tile += n_units) {
         for (int l = 0; l < 8; ++l) {
           const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
-          mbar_wait_cluster(a_ready, pa0);       // input k-blocks 0-3 (layer 0: the encoded points) are in shared memory
+          mbar_wait(a_ready, pa0);               // input k-blocks 0-3 (layer 0: the encoded points) are in shared memory
           pa0 ^= 1;
           tc_fence_after();
           const int nu = l == 0 ? 2 : 16;
@@ -1194,7 +1181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
             const int g = u >> 2;
             const int h = l == 0 ? u : (g & 1), kb = l == 0 ? 0 : ((g >> 1) * 4 + (u & 3));
             if (l > 0 && u == 8) {               // input k-blocks 4-7
-              mbar_wait_cluster(a_ready + 8, pa1);
+              mbar_wait(a_ready + 8, pa1);
               pa1 ^= 1;
               tc_fence_after();
             }
@@ -1260,13 +1247,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       fence_proxy_async_smem();
       tc_fence_before();                       // the head epilogue of the previous tile has drained its accumulators
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader_release(a_ready);
+      if (lane == 0) mbar_arrive_leader(a_ready);
       const int mrow = m0 + row;
       for (int l = 0; l < 8; ++l) {
         const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
         const float* bias = p.bias[l];
         const float scale = l == 3 ? 0.70710678118654752440f : 1.0f;
         for (int h = 0; h < 2; ++h) {
+          float4 bq[4];                                        // bias of the next chunk: in flight across the accumulator wait
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + 256 * h + colq + 16 * chalf) + i);
           mbar_wait(acc_full + 8 * h, pacc);
           tc_fence_after();
           float hsum = 0.0f;
@@ -1278,9 +1268,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
             tmem_ld16(acc + (uint32_t)(h * 128 + 16 * c) + lane_sel, v);
             float b[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
-              b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+            for (int i = 0; i < 4; ++i) { b[4 * i] = bq[i].x; b[4 * i + 1] = bq[i].y; b[4 * i + 2] = bq[i].z; b[4 * i + 3] = bq[i].w; }
+            if (cc == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + n + 64) + i);
             }
             if (l == 7) {                                      // sdf head: fixed-order partial dot product with lin8's row 0
 #pragma unroll
@@ -1293,7 +1284,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
               }
               continue;
             }
-            float w[16];
+            float (&w)[16] = v;
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = softplus100(v[i] + b[i]) * scale;
             uint32_t hi[8], lo[8];
@@ -1332,7 +1323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader_release(a_ready + 8 * h);
+            if (lane == 0) mbar_arrive_leader(a_ready + 8 * h);
           }
         }
         pacc ^= 1;
