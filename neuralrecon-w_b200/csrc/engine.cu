@@ -199,10 +199,11 @@ static Planes rows(Planes P, int r0) { return Planes{P.p + (long long)r0 * P.ld,
 // ---------------------------------------------------------------------------------------------
 // forward chunks
 // ---------------------------------------------------------------------------------------------
-// NRW_SDF_FUSED=1: a forward-only chain (encoding, 8 layers, head) runs as ONE kernel with the activations resident in shared
-// memory (gemm_tc.cu::sdf_fused_kernel); two-plane operands on the tcgen05 backend only.  It needs no chunk workspace.
+// A forward-only chain (encoding, 8 layers, head) runs as ONE kernel with the activations resident in shared memory
+// (gemm_tc.cu::sdf_fused_kernel); two-plane operands on the tcgen05 backend only (NRW_SDF_FUSED=0: per-layer launches).
+// It needs no chunk workspace.
 static bool sdf_fused_enabled(const nrw_ctx& c) {
-  static const int fused_chain = getenv("NRW_SDF_FUSED") ? atoi(getenv("NRW_SDF_FUSED")) : 0;
+  static const int fused_chain = getenv("NRW_SDF_FUSED") ? atoi(getenv("NRW_SDF_FUSED")) : 1;
   return fused_chain && c.backend == NRW_GEMM_TCGEN05 && c.n_planes == 2;
 }
 static int sdf_fused_query(nrw_ctx& c, const float* pts, int M, float* sdf, cudaStream_t s) {

@@ -1104,12 +1104,24 @@ __device__ __forceinline__ float pe6_feature(const float (&x)[3], int f) {
   return wi < 3 ? sn : cs;
 }
 
+// MMA unit u of layer l -> (column half h, input k-block kb).  Layer 0 has one k-block: (h0, kb0), (h1, kb0).  Layers 1-7:
+//   units 0-7 : k-blocks 0, 2, 1, 3 for both halves (h0 then h1 per k-block)     - the order in which the previous layer's
+//   units 8-11: half 0 on k-blocks 4, 6, 5, 7 -> commit half 0                      epilogue finishes them (each epilogue warp
+//   units 12-15: half 1 on k-blocks 4, 6, 5, 7 -> commit half 1                     writes an even k-block first, then its odd one)
+__device__ __forceinline__ void fz_unit(int l, int u, int& h, int& kb) {
+  if (l == 0) { h = u; kb = 0; return; }
+  const int seq = (0x3120 >> (4 * ((u < 8 ? (u >> 1) : u) & 3))) & 0xF;      // 0, 2, 1, 3
+  if (u < 8) { h = u & 1; kb = seq; }
+  else { h = (u - 8) >> 2; kb = 4 + seq; }
+}
+__device__ __forceinline__ bool fz_first_kb(int l, int u) { return l == 0 || u < 2; }   // first k-block of an accumulator (no accumulate)
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_kernel(const __grid_constant__ SdfFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FZ_BAR);
   const uint32_t w_full = smem_u32(bars), w_empty = smem_u32(bars + 3), acc_full = smem_u32(bars + 6), a_ready = smem_u32(bars + 8);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);     // a_ready[8]: one barrier per input k-block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -1120,7 +1132,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < FZ_NST; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(a_ready + 8 * i, 32); }   // 16 epilogue warps x 2 CTAs
+    for (int i = 0; i < 2; ++i) mbar_init(acc_full + 8 * i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(a_ready + 8 * i, 16);   // the 8 epilogue warps per CTA that write k-block i, both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -1146,8 +1159,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       for (int l = 0; l < 8; ++l) {
         const int nu = l == 0 ? 2 : 16;
         for (int u = 0; u < nu; ++u) {
-          const int g = u >> 2;
-          const int h = l == 0 ? u : (g & 1), kb = l == 0 ? 0 : ((g >> 1) * 4 + (u & 3));
+          int h, kb;
+          fz_unit(l, u, h, kb);
           mbar_wait(w_empty + 8 * s, ph ^ 1);
           if (issuer) {
             if (leader) mbar_arrive_expect_tx(w_full + 8 * s, 2 * FZ_WSTAGE);
@@ -1169,20 +1182,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       const uint64_t desc_hi = make_sdesc(0, 16, 1024);
       const bool issuer = elect_one();
       int s = 0;
-      uint32_t ph = 0, pa0 = 0, pa1 = 0;
+      uint32_t ph = 0, pa = 0;                   // pa: phase bit of a_ready[kb] at bit kb
       for (int tile = unit; tile < p.n_tiles; tile += n_units) {
         for (int l = 0; l < 8; ++l) {
           const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
-          mbar_wait(a_ready, pa0);               // input k-blocks 0-3 (layer 0: the encoded points) are in shared memory
-          pa0 ^= 1;
-          tc_fence_after();
+          uint32_t seen = 0;                     // k-blocks of this layer's input already waited for
           const int nu = l == 0 ? 2 : 16;
           for (int u = 0; u < nu; ++u) {
-            const int g = u >> 2;
-            const int h = l == 0 ? u : (g & 1), kb = l == 0 ? 0 : ((g >> 1) * 4 + (u & 3));
-            if (l > 0 && u == 8) {               // input k-blocks 4-7
-              mbar_wait(a_ready + 8, pa1);
-              pa1 ^= 1;
+            int h, kb;
+            fz_unit(l, u, h, kb);
+            if (!((seen >> kb) & 1u)) {          // input k-block kb (layer 0: the encoded points) is in shared memory
+              mbar_wait(a_ready + 8 * kb, (pa >> kb) & 1u);
+              pa ^= 1u << kb;
+              seen |= 1u << kb;
               tc_fence_after();
             }
             mbar_wait(w_full + 8 * s, ph);
@@ -1190,7 +1202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
             if (issuer) {
               const uint32_t sa = smem0 + kb * (FZ_ROWS * BK * 2);
               const uint32_t sb = smem0 + FZ_A + s * FZ_WSTAGE;
-              uint32_t accum = kb != 0;
+              uint32_t accum = !fz_first_kb(l, u);
 #pragma unroll
               for (int pr = 0; pr < 3; ++pr) {   // (hi, lo), (lo, hi), (hi, hi): the product order of the per-layer kernels
                 const uint32_t pa = pr == 1 ? 1u : 0u, pb = pr == 0 ? 1u : 0u;
@@ -1246,8 +1258,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       }
       fence_proxy_async_smem();
       tc_fence_before();                       // the head epilogue of the previous tile has drained its accumulators
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(a_ready);
+      epi_bar_sync();                          // every warp's part of the tile is written (and fenced) ...
+      if ((q >> 1) == 0 && lane == 0) mbar_arrive_leader(a_ready);   // ... the 8 warps that own k-block 0 signal it
       const int mrow = m0 + row;
       for (int l = 0; l < 8; ++l) {
         const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
@@ -1316,15 +1328,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
                 *reinterpret_cast<bf16*>(dst + FZ_APLANE + off) = pl;
               }
             }
-          }
-          if (l == 7) {
-            part[row * 16 + h * 8 + (q >> 1) * 4 + chalf] = hsum;
-          } else {
+            // this warp's 32 rows x 16 columns of k-block n / 64 are written: 8 warps per CTA complete a k-block
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader(a_ready + 8 * h);
+            if (lane == 0) mbar_arrive_leader(a_ready + 8 * (n >> 6));
           }
+          if (l == 7) part[row * 16 + h * 8 + (q >> 1) * 4 + chalf] = hsum;
         }
         pacc ^= 1;
       }
