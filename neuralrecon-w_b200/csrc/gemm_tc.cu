@@ -165,6 +165,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait: several may be in flight, tmem_ld_wait() before the first use of any of them
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory descriptor, 128B swizzle, version 1 (sm_100).
 //   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -1264,27 +1276,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
       for (int l = 0; l < 8; ++l) {
         const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
         const float* bias = p.bias[l];
-        const float scale = l == 3 ? 0.70710678118654752440f : 1.0f;
         for (int h = 0; h < 2; ++h) {
-          float4 bq[4];                                        // bias of the next chunk: in flight across the accumulator wait
-#pragma unroll
-          for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + 256 * h + colq + 16 * chalf) + i);
           mbar_wait(acc_full + 8 * h, pacc);
           tc_fence_after();
           float hsum = 0.0f;
-#pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
+          // both of this warp's 16-column chunks leave the TMEM together (one wait), the first bias vector rides along
+          float va[16], vb[16];
+          tmem_ld16_issue(acc + (uint32_t)(h * 128 + 16 * chalf) + lane_sel, va);
+          tmem_ld16_issue(acc + (uint32_t)(h * 128 + 16 * (chalf + 4)) + lane_sel, vb);
+          auto chunk = [&](float (&v)[16], const int cc) {
             const int c = chalf + 4 * cc;
             const int n = 256 * h + colq + 16 * c;             // first of this thread's 16 output columns
-            float v[16];
-            tmem_ld16(acc + (uint32_t)(h * 128 + 16 * c) + lane_sel, v);
             float b[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { b[4 * i] = bq[i].x; b[4 * i + 1] = bq[i].y; b[4 * i + 2] = bq[i].z; b[4 * i + 3] = bq[i].w; }
-            if (cc == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bias + n + 64) + i);
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
+              b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
             }
+            if (cc == 0) tmem_ld_wait();
             if (l == 7) {                                      // sdf head: fixed-order partial dot product with lin8's row 0
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -1294,11 +1303,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
                 hsum = fmaf(softplus100(v[4 * i + 2] + b[4 * i + 2]), hw.z, hsum);
                 hsum = fmaf(softplus100(v[4 * i + 3] + b[4 * i + 3]), hw.w, hsum);
               }
-              continue;
+              return;
             }
             float (&w)[16] = v;
+            if (l == 3) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = softplus100(v[i] + b[i]) * scale;
+              for (int i = 0; i < 16; ++i) w[i] = softplus100(v[i] + b[i]) * 0.70710678118654752440f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = softplus100(v[i] + b[i]) * 1.0f;
+            }
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1330,10 +1344,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_ke
             }
             // this warp's 32 rows x 16 columns of k-block n / 64 are written: 8 warps per CTA complete a k-block
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's reads
-            tc_fence_before();
+            if (cc == 1) tc_fence_before();    // (after the last TMEM read of this accumulator half)
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(a_ready + 8 * (n >> 6));
-          }
+          };
+          chunk(va, 0);
+          chunk(vb, 1);
           if (l == 7) part[row * 16 + h * 8 + (q >> 1) * 4 + chalf] = hsum;
         }
         pacc ^= 1;
