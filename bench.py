@@ -223,17 +223,21 @@ DTYPES = {"bf16": "bf16", "bf16x3": "bf16 (3-product split, fp32 accumulate)", "
 NCU_TRAFFIC = os.path.join(ROOT, "profiles", "gemm_traffic.json")   # written from the round's `ncu --set full` capture
 
 
-def roofline_from_timing(L, out5, n_steps, ms_step, alg_flop_step, peak_tf, peak_src):
+def roofline_from_timing(L, out5, n_steps, ms_step, alg_flop_step, peak_tf, peak_src, workload=None):
     """roofline of the dominant kernel family from the live CUDA-event timing of EVERY tcgen05 GEMM launch."""
     k_ms, k_flop, k_mma, k_n, k_bytes = (out5[i] / n_steps for i in range(5))
     achieved = k_flop / (k_ms * 1e-3) / 1e12
-    traffic = src = None
+    traffic = src = kernel = None
     if os.path.isfile(NCU_TRAFFIC):
         t = json.load(open(NCU_TRAFFIC))
+        t = t.get(workload, t) if workload else t
         traffic, src = t.get("dram_bytes_per_launch"), t.get("source")
+        kernel = t.get("kernel")
     return {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "traffic": traffic, "traffic_source": src, "peak_source": peak_src,
-            "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 GEMM of every dense layer)",
+            "kernel": "sdf_fused_kernel (fused forward-only SDF chain: encoding + 8 tcgen05 layers + head)" if workload == "C5" else
+                      "gemm_tc2_kernel / gemm_tc_kernel / sdf_fused_kernel (tcgen05 GEMM of every dense layer; the sampler's forward-only chains fused)",
+            "traffic_kernel": kernel,
             "launches_per_step": k_n, "kernel_ms_per_step": k_ms, "share_of_step": k_ms / ms_step,
             "algorithmic_tflop_per_step_in_kernel": k_flop / 1e12,
             "algorithmic_hbm_gb_per_step_in_kernel": k_bytes / 1e9,
@@ -336,7 +340,7 @@ def bench_c5(args, rank, world, local):
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         # one rank evaluates n/world queries; the roofline object describes rank 0's kernels
-        roof = roofline_from_timing(L, out5, 1, ms, F_SDF_VALUE * n / world, peak_tf, peak_src)
+        roof = roofline_from_timing(L, out5, 1, ms, F_SDF_VALUE * n / world, peak_tf, peak_src, workload="C5")
         line = {"metric": "SDF grid queries/sec", "value": n / (ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": DTYPES[args.precision], "data": "synthetic", "config": config, "precision_mode": args.precision,
