@@ -3,12 +3,15 @@ path needs (lightning_modules/neuconw_system.py:61-176,337-360; losses.py:21-43;
 train.py:21-25,61), without PyTorch-Lightning.  One process per GPU; data-parallel ranks reduce the
 flat gradient buffer with one NCCL all-reduce."""
 import math
+import os
 
 import torch
 import torch.distributed as dist
 
 from .models import NeRF, NeuconW
 from .renderer import LABEL_IDS, NeuconWRenderer
+
+_SKIP_REDUCE = os.environ.get("NRW_DIAG_SKIP_REDUCE") == "1"     # diagnosis only (scaling analysis): ranks run unsynchronised
 
 SDF_CONFIG = dict(d_in=3, d_out=513, d_hidden=512, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1,
                   geometric_init=True, weight_norm=True, inside_outside=False)
@@ -165,7 +168,7 @@ class TrainSystem:
     def reduce_grads(self, flat, emb_grad):
         """DDP semantics: gradient MEAN over ranks (per-rank loss normalisers stay per-rank).  One collective
         for neuconw + nerf (15.6 MB flat buffer, NCCL over NVLink) and one for the dense embedding gradient."""
-        if self.world_size > 1:
+        if self.world_size > 1 and not _SKIP_REDUCE:
             dist.all_reduce(flat)
             flat.div_(self.world_size)
             if emb_grad is not None:
