@@ -83,7 +83,10 @@ NRW_API int nrw_ctx_bind(nrw_ctx* ctx, void* packed, long long packed_bytes, voi
  * torch.nn.utils.weight_norm recomputes on every call, models/neuconw.py:104-105,256-257). */
 NRW_API int nrw_pack_weights(nrw_ctx* ctx, const float* params, void* stream);
 
-/* ---- NeuconWRenderer.sdf / NeuconW.sdf  (rendering/renderer.py:947-949) ----------------- */
+/* ---- NeuconWRenderer.sdf / NeuconW.sdf  (rendering/renderer.py:947-949) -----------------
+ * With two-plane operands on the tcgen05 backend the whole query is ONE launch of the fused on-chip chain (encoding, 8 layers,
+ * head; 12 B in / 4 B out of HBM per point) and touches no workspace; otherwise it runs chunk by chunk through the bound
+ * workspace.  Results do not depend on how the caller batches the points. */
 NRW_API int nrw_sdf_query(nrw_ctx* ctx, const float* pts /*[n,3]*/, long long n, float* sdf /*[n]*/,
                           void* stream);
 /* NeuconW.forward pieces (models/neuconw.py:339-376): sdf, features' consumer rgb, normals. */
