@@ -1120,12 +1120,31 @@ __device__ __forceinline__ float pe6_feature(const float (&x)[3], int f) {
 //   units 0-7 : k-blocks 0, 2, 1, 3 for both halves (h0 then h1 per k-block)     - the order in which the previous layer's
 //   units 8-11: half 0 on k-blocks 4, 6, 5, 7 -> commit half 0                      epilogue finishes them (each epilogue warp
 //   units 12-15: half 1 on k-blocks 4, 6, 5, 7 -> commit half 1                     writes an even k-block first, then its odd one)
-__device__ __forceinline__ void fz_unit(int l, int u, int& h, int& kb) {
-  if (l == 0) { h = u; kb = 0; return; }
+__host__ __device__ constexpr int fz_unit_packed(int l, int u) {           // h | kb << 4
+  if (l == 0) return u;
   const int seq = (0x3120 >> (4 * ((u < 8 ? (u >> 1) : u) & 3))) & 0xF;      // 0, 2, 1, 3
-  if (u < 8) { h = u & 1; kb = seq; }
-  else { h = (u - 8) >> 2; kb = 4 + seq; }
+  return u < 8 ? ((u & 1) | (seq << 4)) : (((u - 8) >> 2) | ((4 + seq) << 4));
 }
+__device__ __forceinline__ void fz_unit(int l, int u, int& h, int& kb) {
+  const int pk = fz_unit_packed(l, u);
+  h = pk & 0xF;
+  kb = pk >> 4;
+}
+// the schedule the in-place activation update relies on, checked at compile time: every (half, k-block) pair exactly once per
+// layer; both halves have consumed k-blocks 0-3 before half 0 commits (after unit 11); half 1's last unit is unit 15
+constexpr bool fz_schedule_ok() {
+  int seen[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  for (int u = 0; u < 16; ++u) {
+    const int pk = fz_unit_packed(1, u), h = pk & 0xF, kb = pk >> 4;
+    if (h > 1 || kb > 7 || seen[h][kb]) return false;
+    seen[h][kb] = 1;
+    if (u < 8 && kb > 3) return false;                    // units 0-7 read k-blocks 0-3 only ...
+    if (u >= 8 && kb < 4) return false;                   // ... and nothing reads them afterwards
+    if (u >= 8 && h != (u - 8) / 4) return false;         // units 8-11 finish half 0, units 12-15 half 1
+  }
+  return fz_unit_packed(0, 0) == 0 && fz_unit_packed(0, 1) == 1;
+}
+static_assert(fz_schedule_ok(), "fused SDF chain: MMA unit schedule");
 __device__ __forceinline__ bool fz_first_kb(int l, int u) { return l == 0 || u < 2; }   // first k-block of an accumulator (no accumulate)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) sdf_fused_kernel(const __grid_constant__ SdfFusedParams p) {

@@ -31,5 +31,5 @@ with torch.no_grad():
     for _ in range(3):
         s.renderer.sdf(pts)
     e1.record(); torch.cuda.synchronize()
-print("fused" if os.environ.get("NRW_SDF_FUSED") == "1" else "unfused", "n", n, "ms per query", e0.elapsed_time(e1) / 3, "Mq/s", n / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e6)
+print("fused" if os.environ.get("NRW_SDF_FUSED", "1") != "0" else "per-layer", "n", n, "ms per query", e0.elapsed_time(e1) / 3, "Mq/s", n / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e6)
 torch.save(out.cpu(), sys.argv[1])
